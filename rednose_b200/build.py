@@ -1,0 +1,69 @@
+"""nvcc build driver for generated filter libraries and the runtime library.
+
+Stands in for the reference's SCons tool (site_scons/site_tools/rednose_filter.py:27-37:
+run the generator, then link ``lib{target}.so``) with a direct nvcc invocation for
+sm_100a.  Everything is built in-tree so the artefacts travel with the repository.
+"""
+import os
+import shutil
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(PKG_DIR, "csrc")
+INCLUDE_DIR = os.path.abspath(os.path.join(PKG_DIR, "..", "include"))
+GENERATED_DIR = os.path.join(PKG_DIR, "generated")
+
+NVCC_FLAGS = [
+  "-gencode", "arch=compute_100a,code=sm_100a",
+  "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
+  "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def nvcc_path():
+  p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+  if not os.path.exists(p):
+    raise RuntimeError("nvcc not found: rednose_b200 needs the CUDA toolkit to build filter libraries")
+  return p
+
+
+def _newer(target, sources):
+  if not os.path.exists(target):
+    return False
+  t = os.path.getmtime(target)
+  return all(os.path.getmtime(s) <= t for s in sources if os.path.exists(s))
+
+
+def csrc_sources():
+  return [os.path.join(CSRC_DIR, f) for f in sorted(os.listdir(CSRC_DIR))] + [os.path.join(INCLUDE_DIR, "rednose_b200.h")]
+
+
+def compile_filter(folder, name, force=False, verbose=False):
+  """``{folder}/{name}.cu`` -> ``{folder}/lib{name}.so`` (sm_100a)."""
+  src = os.path.join(folder, f"{name}.cu")
+  lib = os.path.join(folder, f"lib{name}.so")
+  if not force and _newer(lib, [src] + csrc_sources()):
+    return lib
+  cmd = [nvcc_path()] + NVCC_FLAGS + ["-Xptxas", "-v", f"-I{CSRC_DIR}", f"-I{INCLUDE_DIR}", "-o", lib, src]
+  res = subprocess.run(cmd, capture_output=True, text=True)
+  with open(os.path.join(folder, f"{name}.ptxas.log"), "w", encoding="utf-8") as f:
+    f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+  if res.returncode != 0:
+    raise RuntimeError(f"nvcc failed for {src}:\n{res.stderr[-4000:]}")
+  if verbose:
+    print(res.stderr)
+  return lib
+
+
+def compile_runtime(force=False):
+  """csrc/runtime.cc -> rednose_b200/librednose_b200.so (registry + native driver)."""
+  src = os.path.join(CSRC_DIR, "runtime.cc")
+  lib = os.path.join(PKG_DIR, "librednose_b200.so")
+  if not force and _newer(lib, [src] + csrc_sources()):
+    return lib
+  cxx = shutil.which("g++") or "g++"
+  cmd = [cxx, "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", f"-I{INCLUDE_DIR}", "-o", lib, src, "-ldl"]
+  res = subprocess.run(cmd, capture_output=True, text=True)
+  if res.returncode != 0:
+    raise RuntimeError(f"g++ failed for {src}:\n{res.stderr[-4000:]}")
+  return lib

@@ -1,0 +1,229 @@
+// rednose_b200 -- host-side templates behind the generated C-ABI of one filter library.
+//
+// The generated lib<name>.so exports (a) the reference's own symbol set
+// (rednose/helpers/ekf_sym.py:149-171: <name>_predict, <name>_update_<kind>, leaf
+// functions, <name>_set_<var>) operating on HOST pointers for ONE filter, and (b)
+// batched additions (<name>_batch_*) operating on DEVICE pointers.  Both run the same
+// CUDA kernels; there is no CPU implementation in this library.
+#pragma once
+#include "ekf_common.cuh"
+#include "ekf_thread.cuh"
+#include "ekf_warp.cuh"
+#include "ekf_cta.cuh"
+#include <cstring>
+#include <mutex>
+
+namespace rnb {
+
+// placeholder kind for predict-only instantiations
+struct NullKind {
+  static constexpr int KIND = -1, ZDIM = 1, YDIM = 1, EADIM = 0, NH = 0;
+  static constexpr bool MAHA = false, HAS_HE = false;
+  static constexpr double MAHA_THRESH = 0.0;
+  static __device__ __forceinline__ void obs_leaf(const double*, const double*, const double*, double (&)[1], double (&)[1]) {}
+  template <class V> static __device__ __forceinline__ void Herr_apply(const double (&)[1], const V&, double (&)[1]) {}
+  template <class A> static __device__ __forceinline__ void S_accum(const double (&)[1], A, double (&)[1][1]) {}
+};
+
+template <int NG>
+struct GV { double v[NG > 0 ? NG : 1]; };
+
+// Per-library host context: global_vars (ekf_sym.py:129-132 keeps them as file
+// statics; here they are copied into every launch's argument block) and a small
+// device scratch used by the single-filter host-pointer entry points.
+template <class M>
+struct HostCtx {
+  GV<M::NG> gv{};
+  std::mutex mu;
+  double* d_scratch = nullptr;
+  size_t scratch_doubles = 0;
+  cudaStream_t stream = nullptr;
+
+  double* scratch(size_t n) {
+    if (n > scratch_doubles) {
+      if (d_scratch) cudaFree(d_scratch);
+      d_scratch = nullptr; scratch_doubles = 0;
+      if (!check(cudaMalloc(&d_scratch, n * sizeof(double)), "cudaMalloc(scratch)")) return nullptr;
+      scratch_doubles = n;
+    }
+    return d_scratch;
+  }
+};
+
+constexpr int THREAD_MAX_EDIM = 6;
+
+template <class M, class K, bool PRED, bool UPD>
+inline void launch_step(const StepArgs<M::NG>& a, cudaStream_t st) {
+  if (a.B <= 0) return;
+  if constexpr (M::EDIM <= THREAD_MAX_EDIM) {
+    const unsigned grid = (unsigned)((a.B + 127) / 128);
+    ekf_step_thread<M, K, PRED, UPD><<<grid, 128, 0, st>>>(a);
+  } else if constexpr (M::EDIM <= 32) {
+    const unsigned grid = (unsigned)((a.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    ekf_step_warp<M, K, PRED, UPD><<<grid, WARPS_PER_CTA * 32, 0, st>>>(a);
+  } else {
+    launch_step_cta<M, K, PRED, UPD>(a, st);
+  }
+  check(cudaGetLastError(), "ekf_step launch");
+}
+
+template <class M>
+inline void fill_common(StepArgs<M::NG>& a, HostCtx<M>& ctx, long long B, const int* quat_idxs, int n_quat, int flags) {
+  memset(&a, 0, sizeof(a));
+  a.B = B;
+  a.flags = flags;
+  a.n_quat = n_quat < 0 ? 0 : (n_quat > MAX_QUAT ? MAX_QUAT : n_quat);
+  for (int i = 0; i < a.n_quat; ++i) a.quat_idx[i] = quat_idxs[i];
+  for (int i = 0; i < (M::NG > 0 ? M::NG : 1); ++i) a.gv[i] = ctx.gv.v[i];
+  a.n_obs = 1;
+}
+
+// ----------------------------------------------------------- batched (device) ---
+template <class M>
+inline void batch_predict(HostCtx<M>& ctx, double* x, double* P, const double* Q, const double* dt_arr, double dt,
+                          long long B, const int* quat_idxs, int n_quat, int flags,
+                          double* hx_pred, double* hP_pred, void* stream) {
+  StepArgs<M::NG> a;
+  fill_common<M>(a, ctx, B, quat_idxs, n_quat, flags);
+  a.x = x; a.P = P; a.Q = Q; a.dt_arr = dt_arr; a.dt = dt;
+  a.hx_pred = hx_pred; a.hP_pred = hP_pred;
+  launch_step<M, NullKind, true, false>(a, (cudaStream_t)stream);
+}
+
+template <class M, class K, bool PRED>
+inline void batch_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, const double* dt_arr, double dt,
+                       double* z, const double* R, const double* ea, int n_obs, long long B,
+                       const int* quat_idxs, int n_quat, int flags,
+                       double* hx_pred, double* hP_pred, double* hx_filt, double* hP_filt, void* stream) {
+  StepArgs<M::NG> a;
+  fill_common<M>(a, ctx, B, quat_idxs, n_quat, flags);
+  a.x = x; a.P = P; a.Q = Q; a.dt_arr = dt_arr; a.dt = dt;
+  a.z = z; a.R = R; a.ea = (K::EADIM > 0) ? ea : nullptr; a.ea_dim = K::EADIM; a.n_obs = n_obs;
+  a.hx_pred = hx_pred; a.hP_pred = hP_pred; a.hx_filt = hx_filt; a.hP_filt = hP_filt;
+  launch_step<M, K, PRED, true>(a, (cudaStream_t)stream);
+}
+
+// --------------------------------------------- batched, HOST buffers (stateless) ---
+// Full round trip: x,P,z,R(,ea) host -> device, fused step, x,P,y device -> host, in
+// chunks on alternating streams so copies overlap the kernel when the host
+// buffers are pinned.  This is the batched analogue of calling the reference's
+// <name>_predict + <name>_update_<kind> on caller-owned host arrays.
+template <class M, class K>
+inline void host_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, const double* dt_arr, double dt,
+                      double* z, const double* R, const double* ea, int n_obs, long long B,
+                      const int* quat_idxs, int n_quat, int flags) {
+  constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM, EA = K::EADIM;
+  if (B <= 0) return;
+  const long long per = D + E * E + 1 + (long long)n_obs * (Z + Z * Z + EA);
+  long long chunk = (64ll << 20) / (per * 8);  // ~64 MiB of device staging per stream
+  if (chunk < 1) chunk = 1;
+  if (chunk > B) chunk = B;
+  constexpr int NS = 3;
+  static cudaStream_t streams[NS] = {nullptr, nullptr, nullptr};
+  static double* dbuf[NS] = {nullptr, nullptr, nullptr};
+  static long long dcap = 0;
+  static double* dQ = nullptr;
+  std::lock_guard<std::mutex> lk(ctx.mu);
+  for (int i = 0; i < NS; ++i)
+    if (!streams[i] && !check(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking), "cudaStreamCreate")) return;
+  if (!dQ && !check(cudaMalloc(&dQ, sizeof(double) * E * E), "cudaMalloc(Q)")) return;
+  if (chunk * per > dcap) {
+    for (int i = 0; i < NS; ++i) {
+      if (dbuf[i]) cudaFree(dbuf[i]);
+      dbuf[i] = nullptr;
+      if (!check(cudaMalloc(&dbuf[i], sizeof(double) * chunk * per), "cudaMalloc(stage)")) return;
+    }
+    dcap = chunk * per;
+  }
+  if (!check(cudaMemcpy(dQ, Q, sizeof(double) * E * E, cudaMemcpyHostToDevice), "memcpy Q")) return;
+  int si = 0;
+  for (long long b0 = 0; b0 < B; b0 += chunk, si = (si + 1) % NS) {
+    const long long nb = (B - b0 < chunk) ? (B - b0) : chunk;
+    cudaStream_t st = streams[si];
+    double* dx = dbuf[si];
+    double* dP = dx + nb * D;
+    double* ddt = dP + nb * E * E;
+    double* dz = ddt + nb;
+    double* dR = dz + nb * n_obs * Z;
+    double* dea = dR + nb * n_obs * Z * Z;
+    cudaMemcpyAsync(dx, x + b0 * D, sizeof(double) * nb * D, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dP, P + b0 * E * E, sizeof(double) * nb * E * E, cudaMemcpyHostToDevice, st);
+    if (dt_arr) cudaMemcpyAsync(ddt, dt_arr + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dz, z + b0 * n_obs * Z, sizeof(double) * nb * n_obs * Z, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dR, R + b0 * n_obs * Z * Z, sizeof(double) * nb * n_obs * Z * Z, cudaMemcpyHostToDevice, st);
+    if (EA > 0 && ea) cudaMemcpyAsync(dea, ea + b0 * n_obs * EA, sizeof(double) * nb * n_obs * EA, cudaMemcpyHostToDevice, st);
+    StepArgs<M::NG> a;
+    fill_common<M>(a, ctx, nb, quat_idxs, n_quat, flags);
+    a.x = dx; a.P = dP; a.Q = dQ; a.dt_arr = dt_arr ? ddt : nullptr; a.dt = dt;
+    a.z = dz; a.R = dR; a.ea = (EA > 0 && ea) ? dea : nullptr; a.ea_dim = EA; a.n_obs = n_obs;
+    launch_step<M, K, true, true>(a, st);
+    cudaMemcpyAsync(x + b0 * D, dx, sizeof(double) * nb * D, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(P + b0 * E * E, dP, sizeof(double) * nb * E * E, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(z + b0 * n_obs * Z, dz, sizeof(double) * nb * n_obs * Z, cudaMemcpyDeviceToHost, st);
+  }
+  for (int i = 0; i < NS; ++i) check(cudaStreamSynchronize(streams[i]), "host_step sync");
+}
+
+// --------------------------------------------- single filter, HOST pointers ---
+template <class M>
+inline void single_predict(HostCtx<M>& ctx, double* x, double* P, const double* Q, double dt) {
+  constexpr int D = M::DIM, E = M::EDIM;
+  std::lock_guard<std::mutex> lk(ctx.mu);
+  double* d = ctx.scratch(D + 2 * E * E);
+  if (!d) return;
+  double* dx = d; double* dP = d + D; double* dQ = dP + E * E;
+  if (!check(cudaMemcpy(dx, x, sizeof(double) * D, cudaMemcpyHostToDevice), "memcpy x")) return;
+  cudaMemcpy(dP, P, sizeof(double) * E * E, cudaMemcpyHostToDevice);
+  cudaMemcpy(dQ, Q, sizeof(double) * E * E, cudaMemcpyHostToDevice);
+  StepArgs<M::NG> a;
+  fill_common<M>(a, ctx, 1, nullptr, 0, 0);
+  a.x = dx; a.P = dP; a.Q = dQ; a.dt = dt;
+  launch_step<M, NullKind, true, false>(a, nullptr);
+  cudaMemcpy(x, dx, sizeof(double) * D, cudaMemcpyDeviceToHost);
+  check(cudaMemcpy(P, dP, sizeof(double) * E * E, cudaMemcpyDeviceToHost), "memcpy P back");
+}
+
+template <class M, class K>
+inline void single_update(HostCtx<M>& ctx, double* x, double* P, double* z, const double* R, const double* ea) {
+  constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM, EA = K::EADIM;
+  std::lock_guard<std::mutex> lk(ctx.mu);
+  double* d = ctx.scratch(D + E * E + Z + Z * Z + (EA > 0 ? EA : 1));
+  if (!d) return;
+  double* dx = d; double* dP = d + D; double* dz = dP + E * E; double* dR = dz + Z; double* dea = dR + Z * Z;
+  if (!check(cudaMemcpy(dx, x, sizeof(double) * D, cudaMemcpyHostToDevice), "memcpy x")) return;
+  cudaMemcpy(dP, P, sizeof(double) * E * E, cudaMemcpyHostToDevice);
+  cudaMemcpy(dz, z, sizeof(double) * Z, cudaMemcpyHostToDevice);
+  cudaMemcpy(dR, R, sizeof(double) * Z * Z, cudaMemcpyHostToDevice);
+  if (EA > 0 && ea) cudaMemcpy(dea, ea, sizeof(double) * EA, cudaMemcpyHostToDevice);
+  StepArgs<M::NG> a;
+  fill_common<M>(a, ctx, 1, nullptr, 0, 0);
+  a.x = dx; a.P = dP; a.z = dz; a.R = dR; a.ea = (EA > 0 && ea) ? dea : nullptr; a.ea_dim = EA;
+  launch_step<M, K, false, true>(a, nullptr);
+  cudaMemcpy(x, dx, sizeof(double) * D, cudaMemcpyDeviceToHost);
+  cudaMemcpy(P, dP, sizeof(double) * E * E, cudaMemcpyDeviceToHost);
+  // ekf_c.c:120: the innovation overwrites z (K::YDIM entries: ZDIM, or ZDIM-EADIM after projection)
+  check(cudaMemcpy(z, dz, sizeof(double) * K::YDIM, cudaMemcpyDeviceToHost), "memcpy y back");
+}
+
+// leaf functions exported with host pointers (ekf_sym.py:155-161): one-thread kernels
+template <class M, class Kern>
+inline void run_leaf(HostCtx<M>& ctx, Kern kern, const double* in0, int n0, const double* in1, int n1, double s,
+                     double* out, int nout) {
+  std::lock_guard<std::mutex> lk(ctx.mu);
+  double* d = ctx.scratch((size_t)n0 + n1 + nout + 2);
+  if (!d) return;
+  double* d0 = d; double* d1 = d + n0; double* dout = d1 + n1;
+  if (n0 > 0 && !check(cudaMemcpy(d0, in0, sizeof(double) * n0, cudaMemcpyHostToDevice), "leaf memcpy")) return;
+  if (n1 > 0 && in1) cudaMemcpy(d1, in1, sizeof(double) * n1, cudaMemcpyHostToDevice);
+  kern<<<1, 32>>>(d0, d1, s, ctx.gv, dout);
+  check(cudaGetLastError(), "leaf launch");
+  check(cudaMemcpy(out, dout, sizeof(double) * nout, cudaMemcpyDeviceToHost), "leaf memcpy back");
+}
+
+}  // namespace rnb
+
+#define RNB_LEAF_KERNEL(KNAME, NGV, CALL)                                                              \
+  __global__ void KNAME(const double* in0, const double* in1, double s, rnb::GV<NGV> gvs, double* out) { \
+    const double* gv = gvs.v; (void)gv; (void)in1; (void)s;                                            \
+    if (threadIdx.x == 0) { CALL; }                                                                    \
+  }

@@ -1,0 +1,114 @@
+// rednose_b200 -- common device/host helpers for the batched EKF kernels (sm_100a).
+//
+// Hot path being replaced: rednose/templates/ekf_c.c:8-33 (predict) and :37-121 (update),
+// plus the driver-level quaternion normalisation rednose/helpers/ekf_sym.cc:69-77.
+// All arithmetic is IEEE float64, all matrices row-major (ekf_c.c:4-6).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+
+namespace rnb {
+
+constexpr int MAX_QUAT = 8;
+
+// runtime flags of a batched step
+enum : int {
+  FLAG_NORM_AFTER_PREDICT = 1,  // ekf_sym.cc:207 (the C++ driver does, the python driver does not)
+  FLAG_NORM_AFTER_UPDATE  = 2,  // ekf_sym.cc:213 / ekf_sym.py:521
+};
+
+// One argument block per launch, passed by value (lives in the kernel parameter
+// constant bank: every field is warp-uniform).  NG = number of global_vars.
+template <int NG>
+struct StepArgs {
+  double* x;             // [B, DIM]        in/out
+  double* P;             // [B, EDIM, EDIM] in/out, row-major, symmetric
+  const double* Q;       // [EDIM, EDIM]    batch-shared process noise (ekf_c.c:21,28)
+  const double* dt_arr;  // [B] or nullptr -> use dt
+  double dt;
+  double* z;             // [B, n_obs, ZDIM] in/out: overwritten with the innovation y (ekf_c.c:120)
+  const double* R;       // [B, n_obs, ZDIM, ZDIM]
+  const double* ea;      // [B, n_obs, EADIM] or nullptr
+  int n_obs;
+  int ea_dim;            // doubles of extra args per observation (0 if unused)
+  long long B;
+  int flags;
+  int n_quat;
+  int quat_idx[MAX_QUAT];
+  // optional history slabs for the RTS smoother (ekf_sym.py:510,523): written when non-null
+  double* hx_pred;       // [B, DIM]        x_{k|k-1}
+  double* hP_pred;       // [B, EDIM, EDIM] P_{k|k-1}
+  double* hx_filt;       // [B, DIM]        x_{k|k}
+  double* hP_filt;       // [B, EDIM, EDIM] P_{k|k}
+  double gv[NG > 0 ? NG : 1];
+};
+
+// ---------------------------------------------------------------------------
+// Small symmetric solve used for S = H P H^T + R (ZDIM <= ~8 here).
+// The reference uses Eigen fullPivLu (ekf_c.c:89,101); S is symmetric positive
+// definite for any valid R, so an LDL^T factorisation (no square roots, Z
+// reciprocals) gives the same solution to rounding.  Everything is unrolled at
+// compile time so L/D live in registers.
+// ---------------------------------------------------------------------------
+template <int Z>
+struct LDL {
+  double L[Z][Z];   // unit lower (only i>j used)
+  double D[Z];
+  double Dinv[Z];
+
+  __device__ __forceinline__ void factor(const double (&S)[Z][Z]) {
+#pragma unroll
+    for (int j = 0; j < Z; ++j) {
+      double d = S[j][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
+      D[j] = d;
+      Dinv[j] = 1.0 / d;
+#pragma unroll
+      for (int i = j + 1; i < Z; ++i) {
+        double s = S[i][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k] * D[k];
+        L[i][j] = s * Dinv[j];
+      }
+    }
+  }
+  // in-place solve S w = v
+  __device__ __forceinline__ void solve(double (&v)[Z]) const {
+#pragma unroll
+    for (int i = 1; i < Z; ++i) {
+#pragma unroll
+      for (int k = 0; k < i; ++k) v[i] -= L[i][k] * v[k];
+    }
+#pragma unroll
+    for (int i = 0; i < Z; ++i) v[i] *= Dinv[i];
+#pragma unroll
+    for (int i = Z - 2; i >= 0; --i) {
+#pragma unroll
+      for (int k = i + 1; k < Z; ++k) v[i] -= L[k][i] * v[k];
+    }
+  }
+};
+
+// quaternion normalisation of x[idx..idx+4) -- division, like Eigen's normalize()
+__device__ __forceinline__ void normalize4(double* q) {
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+
+// ------------------------------------------------------------------ host ---
+// C-ABI entry points return void (like the reference); failures are recorded
+// here, printed, and surfaced by <name>_cuda_status() so bindings can raise.
+inline int& last_status() { static int s = 0; return s; }
+
+inline bool check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  last_status() = (int)e;
+  fprintf(stderr, "[rednose_b200] CUDA failure in %s: %s\n", what, cudaGetErrorString(e));
+  if (getenv("REDNOSE_B200_ABORT_ON_ERROR")) abort();
+  return false;
+}
+
+}  // namespace rnb
