@@ -1,0 +1,402 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: fused EKF predict+update steps/s over a batch of independent filters.
+
+  python bench.py --gpus N --steps K --warmup W            # this engine on N B200s (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's C path on the host cores
+
+One "step" = one launch of <name>_batch_step_<kind> over the whole per-GPU batch: for every filter
+one predict(dt) + one update_<kind> (rednose/templates/ekf_c.c:8-33 + :37-121).  Workloads
+(BASELINE.json configs / north_star):
+
+  live_1m       1,048,576 live_kf filters (DIM 23 / EDIM 22) per GPU, IMU stream alternating
+                PHONE_GYRO (4) / PHONE_ACCEL (10) at 100 Hz plus an ECEF_POS fix (12) every 100 steps
+  live_100k     same with 100,000 filters            kinematic_1m   1,048,576 kinematic filters, kind 1
+
+Prints ONE JSON line (rank 0).  `value` is the device-resident throughput; `e2e` goes through the public
+BatchedEKF.predict_and_update_batch call with observations in pinned HOST memory and the state estimate
+copied back every step; `roofline` is the dominant kernel against the measured HBM peak; `cpu_baseline`
+is the oracle's reference-equivalent C path on the host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+  "live_1m": dict(filter="live", batch=1 << 20),
+  "live_100k": dict(filter="live", batch=100_000),
+  "kinematic_1m": dict(filter="kinematic", batch=1 << 20),
+}
+LIVE_R = {4: [0.025**2] * 3, 10: [0.5**2] * 3, 12: [5.0**2] * 3}
+L2_BYTES = 126 << 20
+
+
+def bytes_per_step(dim, edim, m, ea=0):
+  """ALGORITHMIC bytes of one fused step: P and x read+written, z and R read, y written, dt read."""
+  return 8 * (2 * edim * edim + 2 * dim + m + m * m + m + ea + 1)
+
+
+def measured_peaks():
+  try:
+    with open(os.path.join(REPO, "MEASURED_PEAKS.json"), encoding="utf-8") as f:
+      return float(json.load(f)["hbm_gbs"]), "measured"
+  except Exception:  # pylint: disable=broad-except
+    return 6650.0, "fallback"
+
+
+def kind_schedule(filter_name, n):
+  if filter_name == "kinematic":
+    return [1] * n
+  return [12 if i % 100 == 0 else (4 if i % 2 else 10) for i in range(n)]
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+  Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+  def __init__(self, gpu_index):
+    self.rows, self.proc, self.idx = [], None, gpu_index
+
+  def __enter__(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+    return self
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(",")])
+
+  def __exit__(self, *a):
+    if self.proc:
+      time.sleep(0.15)
+      self.proc.terminate()
+      self.thread.join(timeout=2)
+
+  def summary(self):
+    sm, mx, reasons = [], [], set()
+    for r in self.rows:
+      try:
+        sm.append(float(r[0])); mx.append(float(r[1]))
+      except (ValueError, IndexError):
+        continue
+      for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+        if v.lower().startswith("active"):
+          reasons.add(name)
+    if not sm:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- synthetic problem ---
+def make_problem(filter_name, B, seed, lib_dir):
+  """Synthetic states/covariances and per-kind observation pools (host numpy).  The observation mean
+  h_k(x_true) is obtained through the product's own leaf entry points (<name>_h_<k>, one filter)."""
+  rng = np.random.default_rng(seed)
+  if filter_name == "kinematic":
+    from rednose_b200.filters.kinematic import KinematicKalman as F
+    x = np.tile(F.initial_x, (B, 1)) + rng.normal(size=(B, 2))
+    P = np.tile(np.diag(F.initial_P_diag), (B, 1, 1))
+    pools = {1: (rng.normal(0.0, 0.1, (4, B, 1)), np.tile(np.array([[0.1**2]]), (B, 1, 1)))}
+    return x, P, F.Q.copy(), pools, (2, 2), []
+  from rednose_b200.ekf_sym import EKF_sym
+  from rednose_b200.filters.live import LiveKalman as F
+  x_true = F.initial_x.copy()
+  x_true[3:7] = [0.7, 0.1, -0.5, 0.5]
+  x_true[3:7] /= np.linalg.norm(x_true[3:7])
+  kf = EKF_sym(lib_dir, "live", F.Q, F.initial_x, np.diag(F.initial_P_diag), 23, 22)
+  x = np.tile(x_true, (B, 1))
+  x[:, 0:3] += rng.normal(0, 10.0, (B, 3))
+  x[:, 7:10] += rng.normal(0, 1.0, (B, 3))
+  x[:, 10:13] += rng.normal(0, 0.05, (B, 3))
+  x[:, 17:20] += rng.normal(0, 0.3, (B, 3))
+  pdiag = np.array([25.0] * 3 + [0.05**2] * 3 + [1.0] * 3 + [0.1**2] * 3 + [0.01**2] * 3 + [0.01**2] + [0.5**2] * 3 + [0.01**2] * 3)
+  P = np.tile(np.diag(pdiag), (B, 1, 1))
+  pools = {}
+  for k, rdiag in LIVE_R.items():
+    hz = np.zeros(3)
+    kf.hs[k](x_true, np.zeros(1), hz)
+    noise = rng.normal(size=(2, B, 3)) * np.sqrt(np.array(rdiag))
+    pools[k] = (hz[None, None, :] + noise, np.tile(np.diag(rdiag), (B, 1, 1)))
+  return x, P, F.Q.copy(), pools, (23, 22), [3]
+
+
+# ----------------------------------------------------------------------------------- GPU arm ---
+def run_gpu(args):
+  import torch
+  import torch.distributed as dist
+  from rednose_b200.batched import BatchedEKF
+  from rednose_b200.filters import ensure_generated
+
+  wl = WORKLOADS[args.workload]
+  fname, B = wl["filter"], (args.batch or wl["batch"])
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if world != args.gpus:
+    if world == 1 and args.gpus > 1:
+      raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+  if fname == "kinematic":
+    from rednose_b200.filters.kinematic import KinematicKalman as FilterCls
+  else:
+    from rednose_b200.filters.live import LiveKalman as FilterCls
+  lib_dir = ensure_generated(FilterCls)
+
+  x0, P0, Q, pools, (dim, edim), quat = make_problem(fname, B, seed=1234 + rank, lib_dir=lib_dir)
+  eng = BatchedEKF(lib_dir, fname, Q, x0, P0, device=dev, quaternion_idxs=quat)
+  dpools = {k: (torch.as_tensor(z).to(dev), torch.as_tensor(R).to(dev)) for k, (z, R) in pools.items()}
+  dt_arr = torch.full((B,), 0.01, dtype=torch.float64, device=dev)
+  zdim = {k: z.shape[-1] for k, (z, R) in pools.items()}
+  zwork = {k: torch.empty(B, 1, zdim[k], dtype=torch.float64, device=dev) for k in pools}
+
+  sched = kind_schedule(fname, args.warmup + args.steps)
+
+  def one_step(i, kind):
+    zp, R = dpools[kind]
+    zwork[kind][:, 0, :].copy_(zp[i % zp.shape[0]])  # fresh observations (the kernel overwrites z with y)
+    eng.step(kind, dt_arr, zwork[kind], R)
+
+  def sync_all():
+    torch.cuda.synchronize(dev)
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize(dev)
+
+  # ---- device-resident throughput ----
+  for i in range(args.warmup):
+    one_step(i, sched[i])
+  sync_all()
+  ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+  t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  launches0 = eng.launches
+  with ClockSampler(local_rank) as clocks:
+    sync_all()
+    t0.record()
+    for j in range(args.steps):
+      i = args.warmup + j
+      kind = sched[i]
+      zp, R = dpools[kind]
+      zwork[kind][:, 0, :].copy_(zp[i % zp.shape[0]])
+      ev[j][0].record()
+      eng.step(kind, dt_arr, zwork[kind], R)
+      ev[j][1].record()
+    t1.record()
+    sync_all()
+  elapsed_ms = t0.elapsed_time(t1)
+  launches = eng.launches - launches0
+  if world > 1:
+    tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(tmax.item())
+  per_kind = {}
+  for j in range(args.steps):
+    per_kind.setdefault(sched[args.warmup + j], []).append(ev[j][0].elapsed_time(ev[j][1]))
+  assert bool(torch.isfinite(eng.x).all()), "filter diverged during the benchmark"
+
+  # ---- end to end through the public API: observations from pinned host memory, estimates back ----
+  e2e_steps = max(3, min(args.steps, args.e2e_steps))
+  hz = {k: torch.as_tensor(pools[k][0][0]).contiguous().pin_memory() for k in pools}
+  hR = {k: torch.as_tensor(pools[k][1]).contiguous().pin_memory() for k in pools}
+  hx_out = torch.empty(B, dim, dtype=torch.float64).pin_memory()
+  hy_out = {k: torch.empty(B, 1, zdim[k], dtype=torch.float64).pin_memory() for k in pools}
+  eng.filter_time = 0.0
+  tnow = 0.0
+
+  def e2e_step(kind):
+    nonlocal tnow
+    tnow += 0.01
+    xd, yd = eng.predict_and_update_batch(tnow, kind, hz[kind], hR[kind])
+    hx_out.copy_(xd, non_blocking=True)
+    hy_out[kind].copy_(yd, non_blocking=True)
+
+  for i in range(3):
+    e2e_step(sched[i])
+  sync_all()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for j in range(e2e_steps):
+    e2e_step(sched[args.warmup + j])
+  e1.record()
+  sync_all()
+  e2e_ms = e0.elapsed_time(e1)
+  if world > 1:
+    tmax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    e2e_ms = float(tmax.item())
+  h2d = sum(8 * B * (zdim[sched[args.warmup + j]] + zdim[sched[args.warmup + j]]**2) for j in range(e2e_steps)) / e2e_steps
+  d2h = sum(8 * B * (dim + zdim[sched[args.warmup + j]]) for j in range(e2e_steps)) / e2e_steps
+
+  # ---- final gather of the state estimates (the only collective of the system) ----
+  gather_ms = None
+  if world > 1:
+    out = torch.empty(world * B, dim, dtype=torch.float64, device=dev)
+    sync_all()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    dist.all_gather_into_tensor(out, eng.x)
+    g1.record()
+    sync_all()
+    gather_ms = g0.elapsed_time(g1)
+
+  if rank == 0:
+    peak, peak_kind = measured_peaks()
+    dom = max(per_kind, key=lambda k: sum(per_kind[k]))
+    dom_ms = float(np.mean(per_kind[dom]))
+    algo = bytes_per_step(dim, edim, zdim[dom]) * B
+    achieved = algo / (dom_ms * 1e-3) / 1e9
+    total_steps = B * args.steps * world
+    line = {
+      "metric": "fused EKF predict+update steps/s (batched, float64)",
+      "value": total_steps / (elapsed_ms * 1e-3),
+      "unit": "steps/s",
+      "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+      "ms_per_step": elapsed_ms / args.steps,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "f64", "data": "synthetic",
+      "config": {"workload": args.workload, "filter": fname, "filters_per_gpu": B, "dim": dim, "edim": edim,
+                 "kind_schedule": "live: kinds 4/10 alternating + kind 12 every 100 steps" if fname == "live" else "kind 1",
+                 "l2": f"inputs larger than L2 ({8 * B * edim * edim / 2**20:.0f} MiB of P per GPU vs 126 MiB)" if 8 * B * edim * edim > L2_BYTES else "inputs FIT in L2 (126 MiB)",
+                 "sharding": "independent filters per GPU, no data-path collective"},
+      "gpu_launches": launches,
+      "per_kind_ms": {str(k): float(np.mean(v)) for k, v in per_kind.items()},
+      "roofline": {"bound": "hbm", "kernel": f"ekf_step<{fname}, kind {dom}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                   "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_step": bytes_per_step(dim, edim, zdim[dom]),
+                   "traffic": None},
+      "e2e": {"value": B * e2e_steps * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+              "steps": e2e_steps, "what": "BatchedEKF.predict_and_update_batch(t, kind, z_pinned_host, R_pinned_host) + D2H of x and y every step; P stays resident"},
+      "clocks": clocks.summary(),
+    }
+    if gather_ms is not None:
+      line["final_gather_ms"] = gather_ms
+    if not args.no_cpu_baseline and world == 1:
+      line["cpu_baseline"] = cpu_reference(fname, args.workload, budget_s=args.cpu_budget)
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------- reference arm / CPU baseline ---
+def cpu_reference(fname, workload, budget_s=15.0, steps=None):
+  """The reference's C path (oracle/_ref: reference-generated leaf C + Eigen-free restatement of ekf_c.c, g++ -O2)
+  looping predict + update_<kind> per filter on all host cores, on a bounded sample of the same workload."""
+  from oracle import build_ref
+  from oracle.handle import Oracle
+  if build_ref.reference_available():
+    build_ref.build(fname)
+  o = Oracle(build_ref.OUT, fname)
+  cores = os.cpu_count() or 1
+  Bs = 4096
+  x, P, Q, pools, (dim, edim), quat = _cpu_problem(fname, Bs)
+  sched = kind_schedule(fname, 1000)
+  # calibrate, then size the sample for ~budget_s of CPU work
+  t = time.perf_counter()
+  k = sched[1]
+  o.batch_step(k, x, P, Q, 0.01, pools[k][0][0], pools[k][1], quat_idxs=quat, flags=3, nthreads=cores)
+  per_filter_step = (time.perf_counter() - t) / Bs
+  n_steps = steps or 20
+  Bs = int(max(1024, min(200_000, budget_s / (per_filter_step * n_steps))))
+  x, P, Q, pools, (dim, edim), quat = _cpu_problem(fname, Bs)
+  t = time.perf_counter()
+  for i in range(n_steps):
+    k = sched[i]
+    zp, R = pools[k]
+    x, P, _ = o.batch_step(k, x, P, Q, 0.01, zp[i % zp.shape[0]], R, quat_idxs=quat, flags=3, nthreads=cores)
+  el = time.perf_counter() - t
+  assert np.isfinite(x).all()
+  return {"value": Bs * n_steps / el, "unit": "steps/s", "cores": cores, "kind": "port",
+          "sample": f"{Bs} {fname} filters x {n_steps} steps of workload {workload} (same kind schedule), {el:.1f} s",
+          "what": "reference-generated leaf C (rednose gen_code, unmodified) + Eigen-free restatement of ekf_c.c, g++ -O2, threads over filters"}
+
+
+def _cpu_problem(fname, B):
+  # the oracle arm must not touch the CUDA libraries: build the same synthetic problem with the oracle's own h_k
+  rng = np.random.default_rng(99)
+  if fname == "kinematic":
+    from rednose_b200.filters.kinematic import KinematicKalman as F
+    x = np.tile(F.initial_x, (B, 1)) + rng.normal(size=(B, 2))
+    P = np.tile(np.diag(F.initial_P_diag), (B, 1, 1))
+    return x, P, F.Q.copy(), {1: (rng.normal(0.0, 0.1, (4, B, 1)), np.tile(np.array([[0.1**2]]), (B, 1, 1)))}, (2, 2), []
+  from oracle import build_ref
+  from rednose_b200.filters.live import LiveKalman as F
+  from oracle.handle import Oracle
+  o = Oracle(build_ref.OUT, "live")
+  x_true = F.initial_x.copy()
+  x_true[3:7] = [0.7, 0.1, -0.5, 0.5]
+  x_true[3:7] /= np.linalg.norm(x_true[3:7])
+  x = np.tile(x_true, (B, 1))
+  x[:, 0:3] += rng.normal(0, 10.0, (B, 3))
+  x[:, 7:10] += rng.normal(0, 1.0, (B, 3))
+  pdiag = np.array([25.0] * 3 + [0.05**2] * 3 + [1.0] * 3 + [0.1**2] * 3 + [0.01**2] * 3 + [0.01**2] + [0.5**2] * 3 + [0.01**2] * 3)
+  P = np.tile(np.diag(pdiag), (B, 1, 1))
+  pools = {}
+  for k, rdiag in LIVE_R.items():
+    hz = np.zeros(3)
+    o.leaf(f"h_{k}", np.ascontiguousarray(x_true), np.zeros(1), hz)
+    pools[k] = (hz[None, None, :] + rng.normal(size=(2, B, 3)) * np.sqrt(np.array(rdiag)), np.tile(np.diag(rdiag), (B, 1, 1)))
+  return x, P, F.Q.copy(), pools, (23, 22), [3]
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  wl = WORKLOADS[args.workload]
+  fname = wl["filter"]
+  dim, edim = (2, 2) if fname == "kinematic" else (23, 22)
+  # each "step" is a bounded sample; K steps + W warmup must end within a few minutes
+  budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))
+  res = None
+  vals = []
+  for i in range(args.warmup + args.steps):
+    res = cpu_reference(fname, args.workload, budget_s=budget, steps=10)
+    if i >= args.warmup:
+      vals.append(res["value"])
+  v = float(np.mean(vals))
+  res["value"] = v
+  line = {"impl": "reference", "metric": "fused EKF predict+update steps/s (batched, float64)", "value": v, "unit": "steps/s",
+          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "config": {"workload": args.workload, "filter": fname, "dim": dim, "edim": edim},
+          "cpu_baseline": res,
+          "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+  print(json.dumps(line))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=40)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--workload", default="live_1m", choices=sorted(WORKLOADS))
+  ap.add_argument("--batch", type=int, default=0, help="override filters per GPU")
+  ap.add_argument("--e2e-steps", type=int, default=10)
+  ap.add_argument("--cpu-budget", type=float, default=15.0)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3)
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,154 @@
+"""Batched EKF engine: B independent filter instances resident in B200 HBM.
+
+This is the batched counterpart of the reference's per-instance driver
+(rednose/helpers/ekf_sym.cc:158-219 / ekf_sym.py:484-531): the state ``x[B, DIM]`` and
+covariance ``P[B, EDIM, EDIM]`` (float64, row-major, AoS per filter) live on the device as
+torch tensors -- torch is only the allocator / stream provider -- and every step is ONE launch of
+the generated library's fused ``<name>_batch_step_<kind>`` kernel through its C-ABI.
+
+Semantics follow the C++ driver: predict(dt) -> [normalise quaternions] -> update(kind) ->
+[normalise] (ekf_sym.cc:162,207,213); the innovation overwrites ``z`` (ekf_c.c:120).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from rednose_b200.loader import load_code, raise_on_cuda_error
+
+NORM_AFTER_PREDICT = 1
+NORM_AFTER_UPDATE = 2
+
+
+def _as_device(t, device, dtype=torch.float64):
+  if isinstance(t, torch.Tensor):
+    return t.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+  return torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64)).to(device, non_blocking=True)
+
+
+class BatchedEKF:
+  def __init__(self, folder, name, Q, x_initial, P_initial, batch=None, device="cuda", quaternion_idxs=(),
+               norm_after_predict=True, norm_after_update=True, global_vars=None):
+    """x_initial: [DIM] (broadcast to `batch` filters) or [B, DIM]; P_initial: [EDIM, EDIM] or [B, EDIM, EDIM]."""
+    if not torch.cuda.is_available():
+      raise RuntimeError("rednose_b200.BatchedEKF needs a CUDA device (no CPU fallback exists)")
+    self.name = name
+    self.device = torch.device(device)
+    self._ffi, self._lib = load_code(folder, name)
+    ffi = self._ffi
+    x0 = torch.as_tensor(np.asarray(x_initial, dtype=np.float64))
+    P0 = torch.as_tensor(np.asarray(P_initial, dtype=np.float64))
+    if x0.ndim == 1:
+      assert batch is not None, "batch size needed when broadcasting a single initial state"
+      x0 = x0.expand(batch, -1)
+    B = x0.shape[0]
+    if P0.ndim == 2:
+      P0 = P0.expand(B, -1, -1)
+    self.B, self.dim_x, self.dim_err = B, x0.shape[1], P0.shape[1]
+    self.x = x0.contiguous().to(self.device).clone()
+    self.P = P0.contiguous().to(self.device).clone()
+    self.Q = _as_device(Q, self.device)
+    assert self.Q.shape == (self.dim_err, self.dim_err)
+    self.filter_time = None  # scalar time shared by the batch, or a [B] tensor
+    self._quat = ffi.new("int[]", list(quaternion_idxs) or [0])
+    self._nquat = len(quaternion_idxs)
+    self.flags = (NORM_AFTER_PREDICT if norm_after_predict else 0) | (NORM_AFTER_UPDATE if norm_after_update else 0)
+    self.kinds = sorted(int(s[len(name) + 12:]) for s in dir(self._lib) if s.startswith(f"{name}_batch_step_"))
+    self._zdim = {}
+    self.launches = 0  # kernels launched through this object (bench.py reports it)
+    for g, v in (global_vars or {}).items():
+      getattr(self._lib, f"{name}_set_{g}")(float(v))
+
+  # ----------------------------------------------------------------- helpers ---
+  def _p(self, t):
+    return self._ffi.cast("double *", t.data_ptr()) if t is not None else self._ffi.NULL
+
+  def _cp(self, t):
+    return self._ffi.cast("const double *", t.data_ptr()) if t is not None else self._ffi.NULL
+
+  def _stream(self):
+    return self._ffi.cast("void *", torch.cuda.current_stream(self.device).cuda_stream)
+
+  def _check(self, what):
+    raise_on_cuda_error(self._lib, self.name, what)
+
+  def _dt_args(self, dt):
+    if isinstance(dt, torch.Tensor):
+      dt = dt.to(self.device, torch.float64).contiguous()
+      assert dt.shape == (self.B,)
+      return dt, self._cp(dt), 0.0
+    return None, self._ffi.NULL, float(dt)
+
+  # ------------------------------------------------------------------- steps ---
+  def predict(self, dt, hist=None):
+    """P <- F P F^T + dt Q, x <- f(x, dt) for the whole batch (ekf_c.c:8-33)."""
+    keep, dt_ptr, dt_s = self._dt_args(dt)
+    hx, hP = (hist if hist is not None else (None, None))
+    with torch.cuda.device(self.device):
+      getattr(self._lib, f"{self.name}_batch_predict")(
+        self._p(self.x), self._p(self.P), self._cp(self.Q), dt_ptr, dt_s, self.B, self._quat, self._nquat, self.flags,
+        self._p(hx), self._p(hP), self._stream())
+    self.launches += 1
+    self._check("batch_predict")
+
+  def _obs_args(self, z, R, ea):
+    z = _as_device(z, self.device)
+    R = _as_device(R, self.device)
+    if z.ndim == 2:
+      z = z.unsqueeze(1)
+    if R.ndim == 3:
+      R = R.unsqueeze(1)
+    assert z.shape[0] == self.B and R.shape[:2] == z.shape[:2] and R.shape[2] == R.shape[3] == z.shape[2]
+    ea = _as_device(ea, self.device) if ea is not None else None
+    return z, R, ea, z.shape[1]
+
+  def update(self, kind, z, R, ea=None, hist=None):
+    """Measurement update of one kind for the whole batch (ekf_c.c:37-121); returns the innovations y [B, n, m]."""
+    z, R, ea, n_obs = self._obs_args(z, R, ea)
+    hx, hP = (hist if hist is not None else (None, None))
+    with torch.cuda.device(self.device):
+      getattr(self._lib, f"{self.name}_batch_update_{kind}")(
+        self._p(self.x), self._p(self.P), self._p(z), self._cp(R), self._cp(ea), n_obs, self.B,
+        self._quat, self._nquat, self.flags, self._p(hx), self._p(hP), self._stream())
+    self.launches += 1
+    self._check(f"batch_update_{kind}")
+    return z
+
+  def step(self, kind, dt, z, R, ea=None, hist_pred=None, hist_filt=None):
+    """Fused predict(dt) + update(kind): one kernel launch, P read and written once."""
+    keep, dt_ptr, dt_s = self._dt_args(dt)
+    z, R, ea, n_obs = self._obs_args(z, R, ea)
+    hxp, hPp = (hist_pred if hist_pred is not None else (None, None))
+    hxf, hPf = (hist_filt if hist_filt is not None else (None, None))
+    with torch.cuda.device(self.device):
+      getattr(self._lib, f"{self.name}_batch_step_{kind}")(
+        self._p(self.x), self._p(self.P), self._cp(self.Q), dt_ptr, dt_s, self._p(z), self._cp(R), self._cp(ea),
+        n_obs, self.B, self._quat, self._nquat, self.flags, self._p(hxp), self._p(hPp), self._p(hxf), self._p(hPf),
+        self._stream())
+    self.launches += 1
+    self._check(f"batch_step_{kind}")
+    return z
+
+  # driver-style entry point: time in, observations in (host or device), innovations out
+  def predict_and_update_batch(self, t, kind, z, R, extra_args=None):
+    """All B filters observe `kind` at time t (scalar or [B]); returns (x [B,DIM] device, y [B,n,m] device)."""
+    if self.filter_time is None:
+      self.filter_time = t
+    dt = t - self.filter_time
+    if not isinstance(dt, torch.Tensor):
+      assert dt >= 0
+    y = self.step(kind, dt, z, R, extra_args)
+    self.filter_time = t
+    return self.x, y
+
+  # -------------------------------------------------------------- host access ---
+  def state(self):
+    return self.x.cpu().numpy()
+
+  def covs(self):
+    return self.P.cpu().numpy()
+
+  def init_state(self, x, P, filter_time=None):
+    self.x.copy_(_as_device(x, self.device).expand_as(self.x))
+    self.P.copy_(_as_device(P, self.device).expand_as(self.P))
+    self.filter_time = filter_time

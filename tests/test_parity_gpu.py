@@ -1,0 +1,190 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle on identical inputs.
+
+Tolerance: per-array max-norm relative error <= 1e-6 (BASELINE.json north_star, float64); the
+structured arithmetic actually agrees to ~1e-11, asserted at 1e-9 so regressions are visible.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.test_oracle_cpu import GOLDEN, P0, Q, X0, run_kinematic_procedure
+from tests.util import LIVE_KINDS, Oracle, kinematic_batch, live_batch, live_obs, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6       # the contract
+TIGHT = 1e-9     # what the implementation achieves on well-conditioned inputs
+
+
+def _engine(gen_dir, name, x, P, Qm, **kw):
+  from rednose_b200.batched import BatchedEKF
+  return BatchedEKF(gen_dir, name, Qm, x, P, **kw)
+
+
+def test_kinematic_golden_through_the_dropin_class(gen_dir):
+  """examples/test_kinematic_kf.py run through EKF_sym_pyx -> C-ABI -> CUDA kernels."""
+  from rednose_b200.filters.kinematic import KinematicKalman
+  kf = KinematicKalman(gen_dir)
+  got = run_kinematic_procedure(kf.filter)
+  for g, want in zip(got, GOLDEN):
+    assert abs(g - want) < 5e-8
+    assert abs(g - want) < 1e-12
+
+
+def test_compare_procedure_on_gpu(gen_dir):
+  from rednose_b200.ekf_sym import EKF_sym
+  from rednose_b200.ekf_sym_pyx import EKF_sym_pyx
+  np.random.seed(0)
+  a = EKF_sym_pyx(gen_dir, "kinematic", Q, X0, P0, 2, 2)
+  b = EKF_sym(gen_dir, "kinematic", Q, X0, P0, 2, 2)
+  ts = np.arange(0, 1, step=0.01)
+  ts[20], ts[40] = ts[40], ts[20]
+  for t in ts:
+    z, R = np.array([[np.random.normal(0, 0.1)]]), np.array([[[0.1**2]]])
+    a.predict_and_update_batch(t, 1, z, R)
+    b.predict_and_update_batch(t, 1, z, R)
+    assert np.allclose(a.state(), b.state()) and np.allclose(a.covs(), b.covs())
+
+
+def test_kinematic_batched_step(gen_dir, oracle_dir):
+  o = Oracle(oracle_dir, "kinematic")
+  B = 10007  # ragged: not a multiple of the CTA size
+  x, P, Qm, z, R = kinematic_batch(B)
+  dt = np.random.default_rng(5).uniform(0.005, 0.02, B)
+  xr, Pr, yr = o.batch_step(1, x, P, Qm, dt, z, R)
+  e = _engine(gen_dir, "kinematic", x, P, Qm)
+  y = e.step(1, torch.as_tensor(dt), z, R)
+  assert rel_err(e.state(), xr) < TIGHT and rel_err(e.covs(), Pr) < TIGHT and rel_err(y.cpu().numpy()[:, 0], yr) < TIGHT
+
+
+@pytest.mark.parametrize("kind", sorted(LIVE_KINDS))
+def test_live_fused_step_every_kind(gen_dir, oracle_dir, kind):
+  o = Oracle(oracle_dir, "live")
+  B = 1031
+  x, P, Qm = live_batch(B, seed=kind)
+  z, R = live_obs(o, kind, x)
+  xr, Pr, yr = o.batch_step(kind, x, P, Qm, 0.01, z, R, quat_idxs=[3], flags=3)
+  e = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  y = e.step(kind, 0.01, z, R)
+  ex, eP, ey = rel_err(e.state(), xr), rel_err(e.covs(), Pr), rel_err(y.cpu().numpy()[:, 0], yr)
+  assert ex < TIGHT and eP < TIGHT and ey < TIGHT, (ex, eP, ey)
+
+
+def test_live_predict_and_update_separately(gen_dir, oracle_dir):
+  o = Oracle(oracle_dir, "live")
+  B = 257
+  x, P, Qm = live_batch(B, seed=11)
+  xr, Pr = o.predict(x, P, Qm, 0.02)
+  e = _engine(gen_dir, "live", x, P, Qm, norm_after_predict=False, norm_after_update=False)
+  e.predict(0.02)
+  assert rel_err(e.state(), xr) < TIGHT and rel_err(e.covs(), Pr) < TIGHT
+  z, R = live_obs(o, 13, xr)
+  xr2, Pr2, yr = o.update(13, xr, Pr, z, R)
+  y = e.update(13, z, R)
+  assert rel_err(e.state(), xr2) < TIGHT and rel_err(e.covs(), Pr2) < TIGHT and rel_err(y.cpu().numpy()[:, 0], yr) < TIGHT
+
+
+def test_live_stream_300_steps(gen_dir, oracle_dir):
+  """IMU at 100 Hz alternating gyro / accel, a position fix at t0 and every 100 steps."""
+  o = Oracle(oracle_dir, "live")
+  B = 64
+  x, P, Qm = live_batch(B, seed=21, well_conditioned=False)  # starts from the example's own P0 scale (cond ~1e12)
+  e = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  xr, Pr = x.copy(), P.copy()
+  for k in range(300):
+    kind = 12 if k % 100 == 0 else (4 if k % 2 else 10)
+    z, R = live_obs(o, kind, xr, seed=100 + k)
+    xr, Pr, yr = o.batch_step(kind, xr, Pr, Qm, 0.01, z, R, quat_idxs=[3], flags=3)
+    y = e.step(kind, 0.01, z, R)
+    if k in (0, 1, 50, 299):
+      assert rel_err(e.state(), xr) < TOL and rel_err(e.covs(), Pr) < TOL, k
+  assert rel_err(e.state(), xr) < 1e-8 and rel_err(e.covs(), Pr) < 1e-8
+
+
+def test_multiple_observations_per_predict(gen_dir, oracle_dir):
+  """n observations of one kind at one timestamp: predict once, update n times (ekf_sym.cc:174-180)."""
+  o = Oracle(oracle_dir, "live")
+  B, n = 129, 3
+  x, P, Qm = live_batch(B, seed=31)
+  zs, Rs = zip(*[live_obs(o, 4, x, seed=40 + i) for i in range(n)])
+  xr, Pr = o.predict(x, P, Qm, 0.01)
+  for i in range(n):
+    xr, Pr, _ = o.update(4, xr, Pr, zs[i], Rs[i])
+  e = _engine(gen_dir, "live", x, P, Qm, norm_after_predict=False, norm_after_update=False)
+  e.step(4, 0.01, np.stack(zs, 1), np.stack(Rs, 1))
+  assert rel_err(e.state(), xr) < TIGHT and rel_err(e.covs(), Pr) < TIGHT
+
+
+def test_leaf_functions_match_reference_generated_c(gen_dir, oracle_dir):
+  from rednose_b200.ekf_sym import EKF_sym
+  from rednose_b200.filters.live import LiveKalman
+  o = Oracle(oracle_dir, "live")
+  kf = EKF_sym(gen_dir, "live", LiveKalman.Q, LiveKalman.initial_x, np.diag(LiveKalman.initial_P_diag), 23, 22)
+  x, _, _ = live_batch(4, seed=7)
+  rng = np.random.default_rng(0)
+  for b in range(4):
+    xb = np.ascontiguousarray(x[b])
+    for fn, shape, args in [("f_fun", 23, (0.01,)), ("F_fun", 22 * 22, (0.01,))]:
+      a, r = np.zeros(shape), np.zeros(shape)
+      getattr(kf, "f" if fn == "f_fun" else "F")(xb, 0.01, a)
+      o.leaf(fn, xb, 0.01, r)
+      assert rel_err(a, r) < 1e-13, fn
+    a, r = np.zeros(23 * 22), np.zeros(23 * 22)
+    kf.H_mod(xb, a); o.leaf("H_mod_fun", xb, r)
+    assert rel_err(a, r) < 1e-13
+    d = rng.normal(0, 0.01, 22)
+    a, r = np.zeros(23), np.zeros(23)
+    kf.err_function(xb, d, a); o.leaf("err_fun", xb, d, r)
+    assert rel_err(a, r) < 1e-13
+    a2, r2 = np.zeros(22), np.zeros(22)
+    kf.inv_err_function(xb, a, a2); o.leaf("inv_err_fun", xb, r, r2)
+    assert rel_err(a2, r2) < 1e-9 and rel_err(a2, d) < 1e-3
+    dummy = np.zeros(1)
+    for k, m in LIVE_KINDS.items():
+      a, r = np.zeros(m), np.zeros(m)
+      kf.hs[k](xb, dummy, a); o.leaf(f"h_{k}", xb, dummy, r)
+      assert rel_err(a, r) < 1e-12, k
+      a, r = np.zeros(m * 23), np.zeros(m * 23)
+      kf.Hs[k](xb, dummy, a); o.leaf(f"H_{k}", xb, dummy, r)
+      assert rel_err(a, r) < 1e-12, k
+
+
+def test_host_buffer_entry_point_equals_device_path(gen_dir):
+  """<name>_host_step_<kind> (host pointers, copies inside) == <name>_batch_step_<kind> (device pointers)."""
+  from rednose_b200.loader import load_code
+  B = 20011
+  x, P, Qm = live_batch(B, seed=3)
+  rng = np.random.default_rng(9)
+  z = x[:, 0:3] + rng.normal(0, 5.0, (B, 3))
+  R = np.tile(np.diag([25.0] * 3), (B, 1, 1))
+  e = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  y = e.step(12, 0.01, z, R).cpu().numpy()[:, 0]
+  ffi, lib = load_code(gen_dir, "live")
+  hx, hP, hz = x.copy(), P.copy(), z.copy()
+  qi = ffi.new("int[]", [3])
+  p = lambda a: ffi.cast("double *", a.ctypes.data)
+  lib.live_host_step_12(p(hx), p(hP), ffi.cast("const double *", Qm.ctypes.data), ffi.NULL, 0.01, p(hz),
+                        ffi.cast("const double *", R.ctypes.data), ffi.NULL, 1, B, qi, 1, 3)
+  assert lib.live_cuda_status() == 0
+  assert np.array_equal(hx, e.state()) and np.array_equal(hP, e.covs()) and np.array_equal(hz, y)
+
+
+def test_full_size_properties_1m_live(gen_dir, oracle_dir):
+  """BASELINE.json full size (1M live filters): size-independent properties + a sampled oracle check."""
+  o = Oracle(oracle_dir, "live")
+  Bu = 4096
+  x, P, Qm = live_batch(Bu, seed=77)
+  z, R = live_obs(o, 4, x)
+  reps = 256  # 4096 * 256 = 1,048,576 filters: every replica must produce bit-identical results
+  B = Bu * reps
+  e = _engine(gen_dir, "live", np.tile(x, (reps, 1)), np.tile(P, (reps, 1, 1)), Qm, quaternion_idxs=[3])
+  y = e.step(4, 0.01, torch.as_tensor(np.tile(z, (reps, 1))), torch.as_tensor(np.tile(R, (reps, 1, 1))))
+  xs = e.x.view(reps, Bu, 23)
+  Ps = e.P.view(reps, Bu, 22, 22)
+  assert bool((xs == xs[0:1]).all()) and bool((Ps == Ps[0:1]).all())       # position independence
+  asym = (e.P - e.P.transpose(1, 2)).abs().amax() / e.P.abs().amax()
+  assert float(asym) < 1e-12                                                # covariance stays symmetric
+  qn = e.x[:, 3:7].norm(dim=1)
+  assert float((qn - 1).abs().max()) < 1e-14                                # quaternion normalised
+  xr, Pr, yr = o.batch_step(4, x, P, Qm, 0.01, z, R, quat_idxs=[3], flags=3)
+  assert rel_err(xs[-1].cpu().numpy(), xr) < TIGHT and rel_err(Ps[-1].cpu().numpy(), Pr) < TIGHT
+  assert B == 1048576
