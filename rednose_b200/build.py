@@ -11,7 +11,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.abspath(os.path.join(PKG_DIR, "..", "include"))
-GENERATED_DIR = os.path.join(PKG_DIR, "generated")
+GENERATED_DIR = os.environ.get("REDNOSE_B200_GENERATED_DIR") or os.path.join(PKG_DIR, "generated")
 
 NVCC_FLAGS = [
   "-gencode", "arch=compute_100a,code=sm_100a",
@@ -44,7 +44,8 @@ def compile_filter(folder, name, force=False, verbose=False):
   lib = os.path.join(folder, f"lib{name}.so")
   if not force and _newer(lib, [src] + csrc_sources()):
     return lib
-  cmd = [nvcc_path()] + NVCC_FLAGS + ["-Xptxas", "-v", f"-I{CSRC_DIR}", f"-I{INCLUDE_DIR}", "-o", lib, src]
+  tune = [f"-D{k}={os.environ[e]}" for k, e in (("RNB_GROUP", "REDNOSE_B200_GROUP"), ("RNB_WARPS", "REDNOSE_B200_WARPS")) if os.environ.get(e)]
+  cmd = [nvcc_path()] + NVCC_FLAGS + tune + ["-Xptxas", "-v", f"-I{CSRC_DIR}", f"-I{INCLUDE_DIR}", "-o", lib, src]
   res = subprocess.run(cmd, capture_output=True, text=True)
   with open(os.path.join(folder, f"{name}.ptxas.log"), "w", encoding="utf-8") as f:
     f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -20,9 +20,9 @@ struct NullKind {
   static constexpr int KIND = -1, ZDIM = 1, YDIM = 1, EADIM = 0, NH = 0;
   static constexpr bool MAHA = false, HAS_HE = false;
   static constexpr double MAHA_THRESH = 0.0;
-  static __device__ __forceinline__ void obs_leaf(const double*, const double*, const double*, double (&)[1], double (&)[1]) {}
-  template <class V> static __device__ __forceinline__ void Herr_apply(const double (&)[1], const V&, double (&)[1]) {}
-  template <class A> static __device__ __forceinline__ void S_accum(const double (&)[1], A, double (&)[1][1]) {}
+  template <class HV> static __device__ __forceinline__ void obs_leaf(const double*, const double*, const double*, double (&)[1], HV&) {}
+  template <class HV, class V> static __device__ __forceinline__ void Herr_apply(const HV&, const V&, double (&hp)[1]) { hp[0] = 0.0; }
+  template <class HV, class A> static __device__ __forceinline__ void S_accum(const HV&, A, double (&)[1][1]) {}
 };
 
 template <int NG>
@@ -59,8 +59,17 @@ inline void launch_step(const StepArgs<M::NG>& a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.B + 127) / 128);
     ekf_step_thread<M, K, PRED, UPD><<<grid, 128, 0, st>>>(a);
   } else if constexpr (M::EDIM <= 32) {
-    const unsigned grid = (unsigned)((a.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    ekf_step_warp<M, K, PRED, UPD><<<grid, WARPS_PER_CTA * 32, 0, st>>>(a);
+    constexpr int G = RNB_GROUP, W = RNB_WARPS;
+    constexpr size_t smem = warp_smem_bytes<M, K, G, W>();
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+      cudaFuncSetAttribute(ekf_step_warp<M, K, PRED, UPD, G, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(ekf_step_warp<M, K, PRED, UPD, G, W>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      configured = true;
+    }
+    const long long per_cta = (long long)G * W;
+    const unsigned grid = (unsigned)((a.B + per_cta - 1) / per_cta);
+    ekf_step_warp<M, K, PRED, UPD, G, W><<<grid, W * 32, smem, st>>>(a);
   } else {
     launch_step_cta<M, K, PRED, UPD>(a, st);
   }

@@ -1,220 +1,335 @@
 // rednose_b200 -- warp-per-filter fused predict+update kernel (6 < EDIM <= 32,
 // e.g. live_kf: DIM 23 / EDIM 22, examples/live_kf.py:97-124).
 //
-// Mapping.  One warp owns one filter.  Lane j holds COLUMN j of the symmetric
-// covariance P in registers (EDIM doubles).  With that ownership
-//   * (F P)[:,j]   = F * P[:,j]            is lane-local  (generated sparse MODEL::F_apply)
-//   * (H P)[:,j]   = Herr * P[:,j]         is lane-local  (generated sparse KIND::Herr_apply)
-//   * W[:,j]       = S^-1 (H P)[:,j]       is lane-local  (row j of the gain K)
-//   * P'[:,j]      = P[:,j] - (H P)^T W[:,j]               needs (H P) broadcast: ZDIM*EDIM doubles
-//                                                           through per-warp shared memory
-//   * F P F^T needs a transposition only for the few rows of F that differ from
-//     the identity (9 of 22 for live_kf): column j of F P F^T = F * (row j of F P)^T,
-//     and row j of F P equals column j of P (symmetry) unless j is such a row.
-//     Those rows go through a [NFROWS][33] shared-memory exchange.
-// The small state x, the innovation and S (ZDIM x ZDIM) are warp-uniform: every
-// lane evaluates the generated leaf code redundantly from shared memory.
+// A warp owns a GROUP of G consecutive filters and walks through three phases:
 //
-// Reference semantics: ekf_c.c:8-33 (predict), :37-121 (update, He==NULL path),
-// normalisation ekf_sym.cc:69-77,207,213.  P is assumed symmetric on entry (it is a
-// covariance; the reference's own arithmetic keeps it symmetric to rounding).
+//  A  (thread-per-filter)  lane l evaluates the generated leaf code of filter l of the group:
+//       x_pred = f(x, dt), the NF non-trivial entries of F, h(x_pred), the NH non-zeros of
+//       H_err = H * H_mod, y = z - h.  Results go to a per-filter ROW in shared memory.  The leaf
+//       code is scalar and branch-free, so 32 lanes = 32 different filters run it at full SIMT
+//       efficiency -- evaluating it redundantly in every lane of a warp-per-filter kernel was the
+//       dominant cost of the first version (profiles/r01_a_*).
+//  B  (warp-per-filter)    for each filter of the group in turn: lane j holds COLUMN j of the
+//       symmetric covariance P in registers.  With that ownership
+//         (F P)[:,j] = F P[:,j]            lane-local  (generated sparse MODEL::F_apply)
+//         (H P)[:,j] = H_err P[:,j]        lane-local  (generated sparse KIND::Herr_apply)
+//         W[:,j]     = S^-1 (H P)[:,j]     lane-local  (row j of the gain K)
+//         P'[:,j]    = P[:,j] - (H P)^T W[:,j]         needs (H P) broadcast through shared memory
+//       F P F^T needs a transposition only for the rows of F that differ from the identity (9 of
+//       22 for live_kf): column j of F P F^T = F (row j of F P)^T, and row j of F P equals column j
+//       of P (symmetry) unless j is such a row; those rows go through a [NFROWS][33] exchange.
+//       Leaf values are read from the filter's row as warp-uniform broadcasts.
+//  C  (thread-per-filter)  lane l injects the correction: x = err_fun(x_pred, K y), normalises
+//       quaternions and writes the state back.
+//
+// Reference semantics: ekf_c.c:8-33 (predict), :37-121 (update, He==NULL path), normalisation
+// ekf_sym.cc:69-77,207,213.  P is assumed symmetric on entry (it is a covariance; the
+// reference's own arithmetic keeps it symmetric to rounding).
 #pragma once
 #include "ekf_common.cuh"
 
 namespace rnb {
 
-constexpr int WARPS_PER_CTA = 4;
+// tuning knobs (overridable at build time: -DRNB_GROUP=..., -DRNB_WARPS=...)
+#ifndef RNB_GROUP
+#define RNB_GROUP 16   // filters per warp group (leaf phase uses RNB_GROUP of the 32 lanes)
+#endif
+#ifndef RNB_WARPS
+#define RNB_WARPS 1    // warps per CTA (warps never synchronise with each other)
+#endif
 
-template <class M, int Z>
-struct WarpScratch {
-  static constexpr int DP = (M::DIM + 1) & ~1;
-  double x[2][DP];                                  // state, double buffered (leaf in -> out)
-  double ex[(M::NFROWS > 0 ? M::NFROWS : 1) * 33];  // row exchange for F P F^T
-  double hp[Z * 32];                                // (H P)[c][k]
-  double dx[32];                                    // error-state correction K y
+constexpr int even_up(int n) { return (n + 1) & ~1; }
+
+// Per-filter row in shared memory.  Every section starts on an even index (16-byte aligned) so
+// rows are moved with 128-bit accesses; the row stride is = 2 (mod 4) doubles, which makes lane-
+// strided 128-bit stores/loads (phase A/C: lane l touches row l) bank-conflict free.
+template <class M, class K>
+struct RowLayout {
+  static constexpr int NFp = even_up(M::NF > 0 ? M::NF : 1);
+  static constexpr int NHp = even_up(K::NH > 0 ? K::NH : 1);
+  static constexpr int Zp = even_up(K::ZDIM);
+  static constexpr int ZZp = even_up(K::ZDIM * K::ZDIM);
+  static constexpr int Dp = even_up(M::DIM);
+  static constexpr int Ep = even_up(M::EDIM);
+  static constexpr int OFF_FV = 0;                  // F value slots; reused for dx = K y once F is dead
+  static constexpr int FVDX = NFp > Ep ? NFp : Ep;
+  static constexpr int OFF_HV = OFF_FV + FVDX;      // H_err value slots
+  static constexpr int OFF_Y = OFF_HV + NHp;        // innovation
+  static constexpr int OFF_R = OFF_Y + Zp;          // measurement noise
+  static constexpr int OFF_X = OFF_R + ZZp;         // predicted state
+  static constexpr int OFF_DT = OFF_X + Dp;         // dt of this filter (+1 pad)
+  static constexpr int RAW = OFF_DT + 2;
+  static constexpr int STRIDE = RAW + ((2 - RAW % 4) + 4) % 4;  // = 2 (mod 4)
 };
 
-template <class M>
-__device__ __forceinline__ void warp_normalize(double* xs, const StepArgs<M::NG>& a, int lane) {
-  for (int q = 0; q < a.n_quat; ++q) {
-    double* qp = xs + a.quat_idx[q];
-    const double n = sqrt(qp[0] * qp[0] + qp[1] * qp[1] + qp[2] * qp[2] + qp[3] * qp[3]);
-    __syncwarp();
-    if (lane < 4) qp[lane] = qp[lane] / n;
-    __syncwarp();
-  }
+template <int N>
+__device__ __forceinline__ void vec_store(double* dst, const double (&v)[N]) {
+  static_assert(N % 2 == 0, "even");
+#pragma unroll
+  for (int i = 0; i < N; i += 2) *reinterpret_cast<double2*>(dst + i) = make_double2(v[i], v[i + 1]);
+}
+template <int N>
+__device__ __forceinline__ void vec_load(const double* src, double (&v)[N]) {
+  static_assert(N % 2 == 0, "even");
+#pragma unroll
+  for (int i = 0; i < N; i += 2) { const double2 t = *reinterpret_cast<const double2*>(src + i); v[i] = t.x; v[i + 1] = t.y; }
 }
 
-template <class M, class K, bool PRED, bool UPD>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) ekf_step_warp(const StepArgs<M::NG> a) {
+template <class M, class K, int G>
+struct WarpScratch {
+  using L = RowLayout<M, K>;
+  alignas(16) double rows[G * L::STRIDE];
+  alignas(16) double ex[(M::NFROWS > 0 ? M::NFROWS : 1) * 33];  // row exchange for F P F^T
+  alignas(16) double hp[K::ZDIM * 32];                          // (H P)[c][k]
+};
+
+// normalise quaternions of a state held in shared memory (private to the calling lane)
+template <int NG>
+__device__ __forceinline__ void lane_normalize(double* xs, const StepArgs<NG>& a) {
+  for (int q = 0; q < a.n_quat; ++q) normalize4(xs + a.quat_idx[q]);
+}
+
+template <class M, class K, bool PRED, bool UPD, int G, int W>
+__global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a) {
   constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM;
+  using L = RowLayout<M, K>;
   static_assert(E <= 32, "warp-per-filter kernel needs EDIM <= 32");
-  __shared__ WarpScratch<M, Z> s_all[WARPS_PER_CTA];
+  static_assert(G <= 32, "group size");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpScratch<M, K, G>& s = reinterpret_cast<WarpScratch<M, K, G>*>(smem_raw)[threadIdx.x >> 5];
 
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const long long b = (long long)blockIdx.x * WARPS_PER_CTA + wib;
-  if (b >= a.B) return;  // whole warp exits together
-  WarpScratch<M, Z>& s = s_all[wib];
+  const long long b0 = ((long long)blockIdx.x * W + (threadIdx.x >> 5)) * G;  // first filter of the group
+  if (b0 >= a.B) return;  // whole warp exits together
+  const int ng = (a.B - b0 < G) ? (int)(a.B - b0) : G;
   const bool act = lane < E;
   const int col = act ? lane : 0;
+  double* myrow = s.rows + (lane < G ? lane : 0) * L::STRIDE;
+  const bool mine = lane < ng;
+  const long long bl = b0 + (mine ? lane : 0);  // this lane's filter in phases A / C
 
-  // ---- loads: column `lane` of P (coalesced 8*E-byte rows), state into smem ----
-  double p[E];
-  {
-    const double* Pg = a.P + b * (long long)(E * E) + col;
-#pragma unroll
-    for (int i = 0; i < E; ++i) p[i] = Pg[i * E];
-  }
-  for (int i = lane; i < D; i += 32) s.x[0][i] = a.x[b * D + i];
-  __syncwarp();
-  double* xs = s.x[0];
-  double* xo = s.x[1];
+  const int n_obs = UPD ? a.n_obs : 1;
+  for (int o = 0; o < n_obs; ++o) {
+    const bool do_pred = PRED && o == 0;
 
-  if constexpr (PRED) {
-    const double dt = a.dt_arr ? a.dt_arr[b] : a.dt;
-    double fv[M::NF > 0 ? M::NF : 1];
-    M::predict_leaf(xs, dt, a.gv, xo, fv);  // all lanes write identical values to xo
-    { double* t = xs; xs = xo; xo = t; }
-
-    // m = F p  (lane-local);  rows of F P that are not rows of P go to the exchange
-    double m[E];
+    // ================= phase A: leaf evaluation, one filter per lane =================
+    if (mine) {
+      double xp[L::Dp];
+      if (o == 0) {
+        double x0[D];
 #pragma unroll
-    for (int i = 0; i < E; ++i) m[i] = p[i];
-    M::F_apply(fv, m);
-    if constexpr (M::NFROWS > 0) {
-      M::frows_store(m, s.ex + lane, 33);
-      __syncwarp();
-      const bool in_rf = (M::FROW_MASK >> lane) & 1u;
-      const int slot = __popc(M::FROW_MASK & ((1u << lane) - 1u));
-      const double* row = s.ex + (in_rf ? slot : 0) * 33;
-      double r[E];
+        for (int i = 0; i < D; ++i) x0[i] = a.x[bl * D + i];
+        if constexpr (PRED) {
+          const double dt = a.dt_arr ? a.dt_arr[bl] : a.dt;
+          double fv[L::NFp];
+          double xn[D];
+          M::predict_leaf(x0, dt, a.gv, xn, fv);
+          if constexpr (L::NFp > M::NF) fv[L::NFp - 1] = 0.0;
+          vec_store(myrow + L::OFF_FV, fv);
+          myrow[L::OFF_DT] = dt;
 #pragma unroll
-      for (int i = 0; i < E; ++i) r[i] = row[i];
-      M::F_apply(fv, r);
+          for (int i = 0; i < D; ++i) xp[i] = xn[i];
+        } else {
 #pragma unroll
-      for (int i = 0; i < E; ++i) p[i] = in_rf ? r[i] : m[i];
-    } else {
+          for (int i = 0; i < D; ++i) xp[i] = x0[i];
+        }
+        if constexpr (L::Dp > D) xp[L::Dp - 1] = 0.0;
+        vec_store(myrow + L::OFF_X, xp);
+        if (PRED && (a.flags & FLAG_NORM_AFTER_PREDICT) && a.n_quat > 0) {
+          lane_normalize(myrow + L::OFF_X, a);
+          vec_load(myrow + L::OFF_X, xp);
+        }
+        if (PRED && a.hx_pred) {
 #pragma unroll
-      for (int i = 0; i < E; ++i) p[i] = m[i];
-    }
-    {
-      const double* Qg = a.Q + col;
+          for (int i = 0; i < D; ++i) a.hx_pred[bl * D + i] = xp[i];
+        }
+      } else {
+        vec_load(myrow + L::OFF_X, xp);  // state after the previous observation of this batch
+      }
+      if constexpr (UPD) {
+        const long long bo = bl * a.n_obs + o;
+        double yr[L::Zp], Rr[L::ZZp];
 #pragma unroll
-      for (int i = 0; i < E; ++i) p[i] = fma(dt, __ldg(Qg + i * E), p[i]);
+        for (int i = 0; i < Z; ++i) yr[i] = a.z[bo * Z + i];
+#pragma unroll
+        for (int i = 0; i < Z * Z; ++i) Rr[i] = a.R[bo * (Z * Z) + i];
+        const double* ea = a.ea ? a.ea + bo * a.ea_dim : nullptr;
+        double hx[Z];
+        double hv[L::NHp];
+        K::obs_leaf(xp, ea, a.gv, hx, hv);
+#pragma unroll
+        for (int i = 0; i < Z; ++i) yr[i] -= hx[i];
+        if constexpr (L::NHp > K::NH) hv[L::NHp - 1] = 0.0;
+        if constexpr (L::Zp > Z) yr[L::Zp - 1] = 0.0;
+        if constexpr (L::ZZp > Z * Z) Rr[L::ZZp - 1] = 0.0;
+        vec_store(myrow + L::OFF_HV, hv);
+        vec_store(myrow + L::OFF_Y, yr);
+        vec_store(myrow + L::OFF_R, Rr);
+#pragma unroll
+        for (int i = 0; i < Z; ++i) a.z[bo * Z + i] = yr[i];  // innovation overwrites z (ekf_c.c:120)
+      }
     }
     __syncwarp();
-    if (a.flags & FLAG_NORM_AFTER_PREDICT) warp_normalize<M>(xs, a, lane);
-    if (a.hx_pred) for (int i = lane; i < D; i += 32) a.hx_pred[b * D + i] = xs[i];
-    if (a.hP_pred && act) {
-      double* Hg = a.hP_pred + b * (long long)(E * E) + col;
-#pragma unroll
-      for (int i = 0; i < E; ++i) Hg[i * E] = p[i];
-    }
-  }
 
-  if constexpr (UPD) {
-    for (int o = 0; o < a.n_obs; ++o) {
-      const long long bo = b * a.n_obs + o;
-      // z, R: identical address in every lane -> one broadcast transaction each
-      double y[Z], R[Z][Z];
+    // ================= phase B: covariance, one filter per warp iteration =================
+#pragma unroll 1
+    for (int f = 0; f < ng; ++f) {
+      const long long b = b0 + f;
+      const double* row = s.rows + f * L::STRIDE;
+      double p[E];
+      {
+        const double* Pg = a.P + b * (long long)(E * E) + col;
 #pragma unroll
-      for (int i = 0; i < Z; ++i) y[i] = a.z[bo * Z + i];
-#pragma unroll
-      for (int i = 0; i < Z; ++i)
-#pragma unroll
-        for (int j = 0; j < Z; ++j) R[i][j] = a.R[bo * (Z * Z) + i * Z + j];
-      const double* ea = a.ea ? a.ea + bo * a.ea_dim : nullptr;
+        for (int i = 0; i < E; ++i) p[i] = Pg[i * E];
+      }
 
-      double hx[Z];
-      double hv[K::NH > 0 ? K::NH : 1];
-      K::obs_leaf(xs, ea, a.gv, hx, hv);
+      if (do_pred) {
+        double fv[L::NFp];
+        vec_load(row + L::OFF_FV, fv);
+        const double dt = row[L::OFF_DT];
+        // m = F p (lane-local); rows of F P that are not rows of P go through the exchange
+        double m[E];
 #pragma unroll
-      for (int i = 0; i < Z; ++i) y[i] -= hx[i];
+        for (int i = 0; i < E; ++i) m[i] = p[i];
+        M::F_apply(fv, m);
+        if constexpr (M::NFROWS > 0) {
+          M::frows_store(m, s.ex + lane, 33);
+          __syncwarp();
+          const bool in_rf = (M::FROW_MASK >> lane) & 1u;
+          const int slot = __popc(M::FROW_MASK & ((1u << lane) - 1u));
+          const double* xr = s.ex + (in_rf ? slot : 0) * 33;
+          double r[E];
+#pragma unroll
+          for (int i = 0; i < E; ++i) r[i] = xr[i];
+          M::F_apply(fv, r);
+#pragma unroll
+          for (int i = 0; i < E; ++i) p[i] = in_rf ? r[i] : m[i];
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int i = 0; i < E; ++i) p[i] = m[i];
+        }
+        const double* Qg = a.Q + col;
+#pragma unroll
+        for (int i = 0; i < E; ++i) p[i] = fma(dt, __ldg(Qg + i * E), p[i]);
+        if (a.hP_pred && act) {
+          double* Hg = a.hP_pred + b * (long long)(E * E) + col;
+#pragma unroll
+          for (int i = 0; i < E; ++i) Hg[i * E] = p[i];
+        }
+      }
 
-      // (H P)[:,lane]
-      double hp[Z];
-      K::Herr_apply(hv, p, hp);
+      if constexpr (UPD) {
+        double hp[Z];
+        double S[Z][Z];
+        {
+          double hv[L::NHp];
+          vec_load(row + L::OFF_HV, hv);
+          K::Herr_apply(hv, p, hp);  // (H P)[:,lane]
 #pragma unroll
-      for (int c = 0; c < Z; ++c) s.hp[c * 32 + lane] = act ? hp[c] : 0.0;
-      __syncwarp();
-
-      // S = Herr (H P)^T + R, warp-uniform
-      double S[Z][Z];
-#pragma unroll
-      for (int i = 0; i < Z; ++i)
-#pragma unroll
-        for (int j = 0; j < Z; ++j) S[i][j] = 0.0;
-      K::S_accum(hv, [&](int c, int k) { return s.hp[c * 32 + k]; }, S);
-
-      LDL<Z> ldl;
-      if constexpr (K::MAHA) {
-        double Sg[Z][Z];
-#pragma unroll
-        for (int i = 0; i < Z; ++i)
-#pragma unroll
-          for (int j = 0; j < Z; ++j) Sg[i][j] = S[i][j] + R[i][j];
-        ldl.factor(Sg);
-        double u[Z];
-#pragma unroll
-        for (int i = 0; i < Z; ++i) u[i] = y[i];
-        ldl.solve(u);
-        double d = 0.0;
-#pragma unroll
-        for (int i = 0; i < Z; ++i) d += y[i] * u[i];
-        if (d > K::MAHA_THRESH) {  // warp-uniform predicate (ekf_c.c:91-93)
+          for (int c = 0; c < Z; ++c) s.hp[c * 32 + lane] = act ? hp[c] : 0.0;
+          __syncwarp();
+          // S = H_err (H P)^T + R, warp-uniform
 #pragma unroll
           for (int i = 0; i < Z; ++i)
 #pragma unroll
-            for (int j = 0; j < Z; ++j) R[i][j] *= 1.0e16;
+            for (int j = 0; j < Z; ++j) S[i][j] = 0.0;
+          K::S_accum(hv, [&](int c, int k) { return s.hp[c * 32 + k]; }, S);
+        }
+        double y[L::Zp], R[L::ZZp];
+        vec_load(row + L::OFF_Y, y);
+        vec_load(row + L::OFF_R, R);
+
+        LDL<Z> ldl;
+        if constexpr (K::MAHA) {
+          double Sg[Z][Z];
+#pragma unroll
+          for (int i = 0; i < Z; ++i)
+#pragma unroll
+            for (int j = 0; j < Z; ++j) Sg[i][j] = S[i][j] + R[i * Z + j];
+          ldl.factor(Sg);
+          double u[Z];
+#pragma unroll
+          for (int i = 0; i < Z; ++i) u[i] = y[i];
+          ldl.solve(u);
+          double d = 0.0;
+#pragma unroll
+          for (int i = 0; i < Z; ++i) d += y[i] * u[i];
+          if (d > K::MAHA_THRESH) {  // warp-uniform predicate (ekf_c.c:91-93)
+#pragma unroll
+            for (int i = 0; i < Z * Z; ++i) R[i] *= 1.0e16;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < Z; ++i)
+#pragma unroll
+          for (int j = 0; j < Z; ++j) S[i][j] += R[i * Z + j];
+        ldl.factor(S);
+
+        // w = S^-1 hp: row `lane` of the Kalman gain;  dx[lane] = K[lane,:] y
+        ldl.solve(hp);
+        double dxl = 0.0;
+#pragma unroll
+        for (int c = 0; c < Z; ++c) dxl = fma(hp[c], y[c], dxl);
+        if (act) const_cast<double*>(row)[L::OFF_FV + lane] = dxl;  // F values are dead: reuse for dx
+
+        // P[:,lane] -= (H P)^T w
+#pragma unroll
+        for (int i = 0; i < E; i += 2) {
+          double a0 = p[i], a1 = (i + 1 < E) ? p[i + 1] : 0.0;
+#pragma unroll
+          for (int c = 0; c < Z; ++c) {
+            const double2 h2 = *reinterpret_cast<const double2*>(&s.hp[c * 32 + i]);
+            a0 = fma(-h2.x, hp[c], a0);
+            a1 = fma(-h2.y, hp[c], a1);
+          }
+          p[i] = a0;
+          if (i + 1 < E) p[i + 1] = a1;
+        }
+        __syncwarp();
+        if (a.hP_filt && act && o == n_obs - 1) {
+          double* Hg = a.hP_filt + b * (long long)(E * E) + col;
+#pragma unroll
+          for (int i = 0; i < E; ++i) Hg[i * E] = p[i];
         }
       }
-#pragma unroll
-      for (int i = 0; i < Z; ++i)
-#pragma unroll
-        for (int j = 0; j < Z; ++j) S[i][j] += R[i][j];
-      ldl.factor(S);
 
-      // w = S^-1 hp : row `lane` of the Kalman gain;  dx[lane] = K[lane,:] y
-      ldl.solve(hp);
-      double dxl = 0.0;
+      if (act) {
+        double* Pg = a.P + b * (long long)(E * E) + col;
 #pragma unroll
-      for (int c = 0; c < Z; ++c) dxl = fma(hp[c], y[c], dxl);
-      s.dx[lane] = act ? dxl : 0.0;
-
-      // P[:,lane] -= (H P)^T w
-#pragma unroll
-      for (int i = 0; i < E; ++i) {
-        double acc = p[i];
-#pragma unroll
-        for (int c = 0; c < Z; ++c) acc = fma(-s.hp[c * 32 + i], hp[c], acc);
-        p[i] = acc;
-      }
-      __syncwarp();
-
-      M::err_fun(xs, s.dx, a.gv, xo);
-      { double* t = xs; xs = xo; xo = t; }
-      __syncwarp();
-      if (a.flags & FLAG_NORM_AFTER_UPDATE) warp_normalize<M>(xs, a, lane);
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < Z; ++i) a.z[bo * Z + i] = y[i];
+        for (int i = 0; i < E; ++i) Pg[i * E] = p[i];
       }
     }
-    if (a.hx_filt) for (int i = lane; i < D; i += 32) a.hx_filt[b * D + i] = xs[i];
-    if (a.hP_filt && act) {
-      double* Hg = a.hP_filt + b * (long long)(E * E) + col;
-#pragma unroll
-      for (int i = 0; i < E; ++i) Hg[i * E] = p[i];
-    }
-  }
+    __syncwarp();
 
-  for (int i = lane; i < D; i += 32) a.x[b * D + i] = xs[i];
-  if (act) {
-    double* Pg = a.P + b * (long long)(E * E) + col;
+    // ================= phase C: inject the correction, one filter per lane =================
+    if (mine) {
+      double xp[L::Dp];
+      vec_load(myrow + L::OFF_X, xp);
+      if constexpr (UPD) {
+        double dx[L::Ep];
+        vec_load(myrow + L::OFF_FV, dx);
+        double xn[L::Dp];
+        M::err_fun(xp, dx, a.gv, xn);
+        if constexpr (L::Dp > D) xn[L::Dp - 1] = 0.0;
+        vec_store(myrow + L::OFF_X, xn);
+        if ((a.flags & FLAG_NORM_AFTER_UPDATE) && a.n_quat > 0) lane_normalize(myrow + L::OFF_X, a);
+        vec_load(myrow + L::OFF_X, xp);
+      }
+      if (o == n_obs - 1) {
 #pragma unroll
-    for (int i = 0; i < E; ++i) Pg[i * E] = p[i];
+        for (int i = 0; i < D; ++i) a.x[bl * D + i] = xp[i];
+        if (UPD && a.hx_filt) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) a.hx_filt[bl * D + i] = xp[i];
+        }
+      }
+    }
+    __syncwarp();
   }
 }
+
+template <class M, class K, int G, int W>
+constexpr size_t warp_smem_bytes() { return sizeof(WarpScratch<M, K, G>) * W; }
 
 }  // namespace rnb
