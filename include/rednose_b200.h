@@ -33,6 +33,7 @@ extern "C" {
 /* step flags (mirrors of the driver-level normalisation calls, ekf_sym.cc:207,213) */
 #define REDNOSE_NORM_AFTER_PREDICT 1
 #define REDNOSE_NORM_AFTER_UPDATE 2
+#define REDNOSE_Q_IS_DIAGONAL 4      /* caller promises Q is diagonal: kernels read only its diagonal */
 
 typedef void (*rednose_leaf3_fn)(double *, double *, double *);
 typedef void (*rednose_leaf2_fn)(double *, double *);

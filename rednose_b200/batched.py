@@ -18,6 +18,7 @@ from rednose_b200.loader import load_code, raise_on_cuda_error
 
 NORM_AFTER_PREDICT = 1
 NORM_AFTER_UPDATE = 2
+Q_IS_DIAGONAL = 4
 
 
 def _as_device(t, device, dtype=torch.float64):
@@ -53,6 +54,9 @@ class BatchedEKF:
     self._quat = ffi.new("int[]", list(quaternion_idxs) or [0])
     self._nquat = len(quaternion_idxs)
     self.flags = (NORM_AFTER_PREDICT if norm_after_predict else 0) | (NORM_AFTER_UPDATE if norm_after_update else 0)
+    Qh = np.asarray(Q, dtype=np.float64) if not isinstance(Q, torch.Tensor) else Q.detach().cpu().numpy()
+    if np.count_nonzero(Qh - np.diag(np.diagonal(Qh))) == 0:
+      self.flags |= Q_IS_DIAGONAL  # lets the kernels skip the dense dt*Q read
     self.kinds = sorted(int(s[len(name) + 12:]) for s in dir(self._lib) if s.startswith(f"{name}_batch_step_"))
     self._zdim = {}
     self.launches = 0  # kernels launched through this object (bench.py reports it)

@@ -59,6 +59,11 @@ inline void launch_step(const StepArgs<M::NG>& a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.B + 127) / 128);
     ekf_step_thread<M, K, PRED, UPD><<<grid, 128, 0, st>>>(a);
   } else if constexpr (M::EDIM <= 32) {
+    if (use_tma<M>() && (reinterpret_cast<uintptr_t>(a.P) & 15u)) {
+      fprintf(stderr, "[rednose_b200] P must be 16-byte aligned (bulk-copy staging of covariance tiles)\n");
+      last_status() = (int)cudaErrorMisalignedAddress;
+      return;
+    }
     constexpr int G = RNB_GROUP, W = RNB_WARPS;
     constexpr size_t smem = warp_smem_bytes<M, K, G, W>();
     static bool configured = false;  // per instantiation
@@ -123,7 +128,7 @@ inline void host_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, co
                       const int* quat_idxs, int n_quat, int flags) {
   constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM, EA = K::EADIM;
   if (B <= 0) return;
-  const long long per = D + E * E + 1 + (long long)n_obs * (Z + Z * Z + EA);
+  const long long per = D + E * E + 1 + (long long)n_obs * (Z + Z * Z + EA) + 1;
   long long chunk = (64ll << 20) / (per * 8);  // ~64 MiB of device staging per stream
   if (chunk < 1) chunk = 1;
   if (chunk > B) chunk = B;
@@ -149,12 +154,13 @@ inline void host_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, co
   for (long long b0 = 0; b0 < B; b0 += chunk, si = (si + 1) % NS) {
     const long long nb = (B - b0 < chunk) ? (B - b0) : chunk;
     cudaStream_t st = streams[si];
+    auto up2 = [](long long n) { return (n + 1) & ~1ll; };  // keep every sub-buffer 16-byte aligned (bulk copies)
     double* dx = dbuf[si];
-    double* dP = dx + nb * D;
-    double* ddt = dP + nb * E * E;
-    double* dz = ddt + nb;
-    double* dR = dz + nb * n_obs * Z;
-    double* dea = dR + nb * n_obs * Z * Z;
+    double* dP = dx + up2(nb * D);
+    double* ddt = dP + up2(nb * E * E);
+    double* dz = ddt + up2(nb);
+    double* dR = dz + up2(nb * n_obs * Z);
+    double* dea = dR + up2(nb * n_obs * Z * Z);
     cudaMemcpyAsync(dx, x + b0 * D, sizeof(double) * nb * D, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(dP, P + b0 * E * E, sizeof(double) * nb * E * E, cudaMemcpyHostToDevice, st);
     if (dt_arr) cudaMemcpyAsync(ddt, dt_arr + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st);

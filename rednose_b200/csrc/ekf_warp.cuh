@@ -32,13 +32,49 @@ namespace rnb {
 
 // tuning knobs (overridable at build time: -DRNB_GROUP=..., -DRNB_WARPS=...)
 #ifndef RNB_GROUP
-#define RNB_GROUP 16   // filters per warp group (leaf phase uses RNB_GROUP of the 32 lanes)
+#define RNB_GROUP 8   // filters per warp group (leaf phase uses RNB_GROUP of the 32 lanes)
 #endif
 #ifndef RNB_WARPS
 #define RNB_WARPS 1    // warps per CTA (warps never synchronise with each other)
 #endif
 
+#ifndef RNB_TMA
+#define RNB_TMA 1      // stage covariance tiles through shared memory with cp.async.bulk (TMA) load + store
+#endif
+#ifndef RNB_STAGES
+#define RNB_STAGES 2   // covariance tile ring per warp = bulk loads in flight per warp
+#endif
+#ifndef RNB_TMA_STORE
+#define RNB_TMA_STORE 0  // 1: results leave through the tile with a bulk store; 0: plain coalesced stores from registers
+#endif
+
 constexpr int even_up(int n) { return (n + 1) & ~1; }
+
+// ---- TMA (cp.async.bulk) + mbarrier primitives; SASS: UBLKCP / SYNCS ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Per-filter row in shared memory.  Every section starts on an even index (16-byte aligned) so
 // rows are moved with 128-bit accesses; the row stride is = 2 (mod 4) doubles, which makes lane-
@@ -75,9 +111,15 @@ __device__ __forceinline__ void vec_load(const double* src, double (&v)[N]) {
   for (int i = 0; i < N; i += 2) { const double2 t = *reinterpret_cast<const double2*>(src + i); v[i] = t.x; v[i + 1] = t.y; }
 }
 
+template <class M>
+constexpr bool use_tma() { return RNB_TMA && ((M::EDIM * M::EDIM) % 2 == 0); }  // bulk copies move multiples of 16 bytes
+
 template <class M, class K, int G>
 struct WarpScratch {
   using L = RowLayout<M, K>;
+  static constexpr int NST = use_tma<M>() ? RNB_STAGES : 0;
+  alignas(128) double tile[(NST > 0 ? NST : 1) * (use_tma<M>() ? M::EDIM * M::EDIM : 2)];  // covariance tiles (TMA ring)
+  alignas(8) uint64_t full[NST > 0 ? NST : 1];                                              // "tile landed" mbarriers
   alignas(16) double rows[G * L::STRIDE];
   alignas(16) double ex[(M::NFROWS > 0 ? M::NFROWS : 1) * 33];  // row exchange for F P F^T
   alignas(16) double hp[K::ZDIM * 32];                          // (H P)[c][k]
@@ -89,13 +131,31 @@ __device__ __forceinline__ void lane_normalize(double* xs, const StepArgs<NG>& a
   for (int q = 0; q < a.n_quat; ++q) normalize4(xs + a.quat_idx[q]);
 }
 
+// cooperative, coalesced copy between a contiguous global block of ng records of width WD and the
+// per-filter rows in shared memory (record f -> rows[f * STRIDE + off .. + WD))
+template <int WD, int STRIDE>
+__device__ __forceinline__ void stage_in(const double* __restrict__ g, double* rows, int off, int ng, int lane) {
+  for (int idx = lane; idx < ng * WD; idx += 32) {
+    const int f = idx / WD, i = idx - f * WD;
+    rows[f * STRIDE + off + i] = g[idx];
+  }
+}
+template <int WD, int STRIDE>
+__device__ __forceinline__ void stage_out(double* __restrict__ g, const double* rows, int off, int ng, int lane) {
+  for (int idx = lane; idx < ng * WD; idx += 32) {
+    const int f = idx / WD, i = idx - f * WD;
+    g[idx] = rows[f * STRIDE + off + i];
+  }
+}
+
 template <class M, class K, bool PRED, bool UPD, int G, int W>
 __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a) {
   constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM;
   using L = RowLayout<M, K>;
+  constexpr int RS = L::STRIDE;
   static_assert(E <= 32, "warp-per-filter kernel needs EDIM <= 32");
   static_assert(G <= 32, "group size");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   WarpScratch<M, K, G>& s = reinterpret_cast<WarpScratch<M, K, G>*>(smem_raw)[threadIdx.x >> 5];
 
   const int lane = threadIdx.x & 31;
@@ -104,84 +164,146 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
   const int ng = (a.B - b0 < G) ? (int)(a.B - b0) : G;
   const bool act = lane < E;
   const int col = act ? lane : 0;
-  double* myrow = s.rows + (lane < G ? lane : 0) * L::STRIDE;
+  double* myrow = s.rows + (lane < G ? lane : 0) * RS;
   const bool mine = lane < ng;
-  const long long bl = b0 + (mine ? lane : 0);  // this lane's filter in phases A / C
+
+  constexpr bool TMA = use_tma<M>();
+  constexpr int NST = TMA ? RNB_STAGES : 1;
+  constexpr uint32_t TILE_BYTES = E * E * sizeof(double);
+  uint32_t it = 0;  // tiles consumed so far by this warp (ring position / mbarrier parity)
+  if constexpr (TMA) {
+    if (lane == 0) {
+#pragma unroll
+      for (int st = 0; st < NST; ++st) mbar_init(&s.full[st], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      fence_async_smem();
+    }
+    __syncwarp();
+  }
+  // producer side of the tile ring: one elected lane arms the barrier and issues the bulk copy
+  auto issue_load = [&](int f, uint32_t slot) {
+    mbar_expect_tx(&s.full[slot], TILE_BYTES);
+    tma_load_1d(s.tile + slot * (E * E), a.P + (b0 + f) * (long long)(E * E), TILE_BYTES, &s.full[slot]);
+  };
+
+  // diagonal process noise: this lane's entry, fetched once per warp
+  double qdiag = 0.0;
+  if (PRED && (a.flags & FLAG_Q_DIAG)) qdiag = __ldg(a.Q + col * E + col);
 
   const int n_obs = UPD ? a.n_obs : 1;
   for (int o = 0; o < n_obs; ++o) {
     const bool do_pred = PRED && o == 0;
+    if constexpr (TMA) {
+      if (o > 0) {
+        // this warp's own plain stores of P (previous observation pass) must be visible to the bulk-copy engine
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncwarp();
+      }
+      // prefetch the first covariance tiles of the group; they land while the leaf phase runs
+      if (lane == 0) {
+        if (RNB_TMA_STORE) tma_store_wait_read();  // (o > 0) tiles of the previous pass must have drained
+#pragma unroll
+        for (int k = 0; k < NST - (RNB_TMA_STORE ? 1 : 0); ++k)
+          if (k < ng) issue_load(k, (it + k) % NST);
+      }
+    }
+
+    // ---- stage this group's small per-filter records into the rows (coalesced) ----
+    if (o == 0) stage_in<D, RS>(a.x + b0 * D, s.rows, L::OFF_X, ng, lane);
+    if constexpr (UPD) {
+      if (a.n_obs == 1) {
+        stage_in<Z, RS>(a.z + b0 * Z, s.rows, L::OFF_Y, ng, lane);
+        stage_in<Z * Z, RS>(a.R + b0 * (Z * Z), s.rows, L::OFF_R, ng, lane);
+      } else if (mine) {
+        const long long bo = (b0 + lane) * a.n_obs + o;
+#pragma unroll
+        for (int i = 0; i < Z; ++i) myrow[L::OFF_Y + i] = a.z[bo * Z + i];
+#pragma unroll
+        for (int i = 0; i < Z * Z; ++i) myrow[L::OFF_R + i] = a.R[bo * (Z * Z) + i];
+      }
+    }
+    __syncwarp();
 
     // ================= phase A: leaf evaluation, one filter per lane =================
     if (mine) {
       double xp[L::Dp];
-      if (o == 0) {
-        double x0[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) x0[i] = a.x[bl * D + i];
-        if constexpr (PRED) {
-          const double dt = a.dt_arr ? a.dt_arr[bl] : a.dt;
-          double fv[L::NFp];
-          double xn[D];
-          M::predict_leaf(x0, dt, a.gv, xn, fv);
-          if constexpr (L::NFp > M::NF) fv[L::NFp - 1] = 0.0;
-          vec_store(myrow + L::OFF_FV, fv);
-          myrow[L::OFF_DT] = dt;
-#pragma unroll
-          for (int i = 0; i < D; ++i) xp[i] = xn[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < D; ++i) xp[i] = x0[i];
-        }
-        if constexpr (L::Dp > D) xp[L::Dp - 1] = 0.0;
-        vec_store(myrow + L::OFF_X, xp);
-        if (PRED && (a.flags & FLAG_NORM_AFTER_PREDICT) && a.n_quat > 0) {
-          lane_normalize(myrow + L::OFF_X, a);
-          vec_load(myrow + L::OFF_X, xp);
-        }
-        if (PRED && a.hx_pred) {
-#pragma unroll
-          for (int i = 0; i < D; ++i) a.hx_pred[bl * D + i] = xp[i];
-        }
-      } else {
-        vec_load(myrow + L::OFF_X, xp);  // state after the previous observation of this batch
+      vec_load(myrow + L::OFF_X, xp);
+      if (do_pred) {
+        const double dt = a.dt_arr ? a.dt_arr[b0 + lane] : a.dt;
+        double fv[L::NFp];
+        double xn[L::Dp];
+        M::predict_leaf(xp, dt, a.gv, xn, fv);
+        if constexpr (L::NFp > M::NF) fv[L::NFp - 1] = 0.0;
+        if constexpr (L::Dp > D) xn[L::Dp - 1] = 0.0;
+        vec_store(myrow + L::OFF_FV, fv);
+        myrow[L::OFF_DT] = dt;
+        vec_store(myrow + L::OFF_X, xn);
+        if ((a.flags & FLAG_NORM_AFTER_PREDICT) && a.n_quat > 0) lane_normalize(myrow + L::OFF_X, a);
+        vec_load(myrow + L::OFF_X, xp);
       }
       if constexpr (UPD) {
-        const long long bo = bl * a.n_obs + o;
-        double yr[L::Zp], Rr[L::ZZp];
-#pragma unroll
-        for (int i = 0; i < Z; ++i) yr[i] = a.z[bo * Z + i];
-#pragma unroll
-        for (int i = 0; i < Z * Z; ++i) Rr[i] = a.R[bo * (Z * Z) + i];
-        const double* ea = a.ea ? a.ea + bo * a.ea_dim : nullptr;
+        const double* ea = a.ea ? a.ea + ((b0 + lane) * a.n_obs + o) * a.ea_dim : nullptr;
         double hx[Z];
         double hv[L::NHp];
         K::obs_leaf(xp, ea, a.gv, hx, hv);
-#pragma unroll
-        for (int i = 0; i < Z; ++i) yr[i] -= hx[i];
         if constexpr (L::NHp > K::NH) hv[L::NHp - 1] = 0.0;
-        if constexpr (L::Zp > Z) yr[L::Zp - 1] = 0.0;
-        if constexpr (L::ZZp > Z * Z) Rr[L::ZZp - 1] = 0.0;
         vec_store(myrow + L::OFF_HV, hv);
-        vec_store(myrow + L::OFF_Y, yr);
-        vec_store(myrow + L::OFF_R, Rr);
 #pragma unroll
-        for (int i = 0; i < Z; ++i) a.z[bo * Z + i] = yr[i];  // innovation overwrites z (ekf_c.c:120)
+        for (int i = 0; i < Z; ++i) myrow[L::OFF_Y + i] -= hx[i];  // innovation y = z - h(x)
       }
     }
     __syncwarp();
+    if (do_pred && a.hx_pred) stage_out<D, RS>(a.hx_pred + b0 * D, s.rows, L::OFF_X, ng, lane);
+    if constexpr (UPD) {
+      // the innovation overwrites z (ekf_c.c:120)
+      if (a.n_obs == 1) {
+        stage_out<Z, RS>(a.z + b0 * Z, s.rows, L::OFF_Y, ng, lane);
+      } else if (mine) {
+        const long long bo = (b0 + lane) * a.n_obs + o;
+#pragma unroll
+        for (int i = 0; i < Z; ++i) a.z[bo * Z + i] = myrow[L::OFF_Y + i];
+      }
+    }
 
     // ================= phase B: covariance, one filter per warp iteration =================
 #pragma unroll 1
     for (int f = 0; f < ng; ++f) {
       const long long b = b0 + f;
-      const double* row = s.rows + f * L::STRIDE;
+      double* row = s.rows + f * RS;
       double p[E];
-      {
+      const uint32_t slot = it % NST;
+      double* tile = s.tile + (TMA ? slot * (E * E) : 0);
+      if constexpr (TMA) {
+        mbar_wait(&s.full[slot], (it / NST) & 1u);
+        // P is symmetric: read ROW `lane` (contiguous, 128-bit accesses) as column `lane`
+        if constexpr (E % 2 == 0) {
+#pragma unroll
+          for (int i = 0; i < E; i += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(tile + col * E + i);
+            p[i] = t.x; p[i + 1] = t.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < E; ++i) p[i] = tile[i * E + col];
+        }
+        if constexpr (RNB_TMA_STORE) {
+          // tile f+NST-1 goes into the slot whose store was issued one iteration ago
+          if (lane == 0 && f + NST - 1 < ng) {
+            tma_store_wait_read();
+            issue_load(f + NST - 1, (it + NST - 1) % NST);
+          }
+        } else {
+          // the slot is free as soon as every lane has its column in registers: refill it at once,
+          // keeping NST bulk loads in flight per warp
+          __syncwarp();
+          if (lane == 0 && f + NST < ng) issue_load(f + NST, slot);
+        }
+      } else {
         const double* Pg = a.P + b * (long long)(E * E) + col;
 #pragma unroll
         for (int i = 0; i < E; ++i) p[i] = Pg[i * E];
       }
+      ++it;
 
       if (do_pred) {
         double fv[L::NFp];
@@ -196,11 +318,15 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
           M::frows_store(m, s.ex + lane, 33);
           __syncwarp();
           const bool in_rf = (M::FROW_MASK >> lane) & 1u;
-          const int slot = __popc(M::FROW_MASK & ((1u << lane) - 1u));
-          const double* xr = s.ex + (in_rf ? slot : 0) * 33;
+          const int slot_rf = __popc(M::FROW_MASK & ((1u << lane) - 1u));
+          const double* xr = s.ex + slot_rf * 33;
           double r[E];
 #pragma unroll
-          for (int i = 0; i < E; ++i) r[i] = xr[i];
+          for (int i = 0; i < E; ++i) r[i] = m[i];
+          if (in_rf) {  // only the lanes owning a non-identity row of F read the exchange
+#pragma unroll
+            for (int i = 0; i < E; ++i) r[i] = xr[i];
+          }
           M::F_apply(fv, r);
 #pragma unroll
           for (int i = 0; i < E; ++i) p[i] = in_rf ? r[i] : m[i];
@@ -209,9 +335,16 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
 #pragma unroll
           for (int i = 0; i < E; ++i) p[i] = m[i];
         }
-        const double* Qg = a.Q + col;
+        if (a.flags & FLAG_Q_DIAG) {
+          // diagonal process noise: only P[lane][lane] changes
+          const double dq = dt * qdiag;
 #pragma unroll
-        for (int i = 0; i < E; ++i) p[i] = fma(dt, __ldg(Qg + i * E), p[i]);
+          for (int i = 0; i < E; ++i) p[i] += (i == lane) ? dq : 0.0;
+        } else {
+          const double* Qg = a.Q + col;
+#pragma unroll
+          for (int i = 0; i < E; ++i) p[i] = fma(dt, __ldg(Qg + i * E), p[i]);
+        }
         if (a.hP_pred && act) {
           double* Hg = a.hP_pred + b * (long long)(E * E) + col;
 #pragma unroll
@@ -271,7 +404,7 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
         double dxl = 0.0;
 #pragma unroll
         for (int c = 0; c < Z; ++c) dxl = fma(hp[c], y[c], dxl);
-        if (act) const_cast<double*>(row)[L::OFF_FV + lane] = dxl;  // F values are dead: reuse for dx
+        if (act) row[L::OFF_FV + lane] = dxl;  // F values are dead: reuse for dx
 
         // P[:,lane] -= (H P)^T w
 #pragma unroll
@@ -294,7 +427,15 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
         }
       }
 
-      if (act) {
+      if constexpr (TMA && RNB_TMA_STORE) {
+        if (act) {
+#pragma unroll
+          for (int i = 0; i < E; ++i) tile[i * E + col] = p[i];
+        }
+        fence_async_smem();  // make the generic-proxy writes visible to the bulk-copy engine
+        __syncwarp();
+        if (lane == 0) tma_store_1d(a.P + b * (long long)(E * E), tile, TILE_BYTES);
+      } else if (act) {
         double* Pg = a.P + b * (long long)(E * E) + col;
 #pragma unroll
         for (int i = 0; i < E; ++i) Pg[i * E] = p[i];
@@ -303,29 +444,26 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
     __syncwarp();
 
     // ================= phase C: inject the correction, one filter per lane =================
-    if (mine) {
-      double xp[L::Dp];
-      vec_load(myrow + L::OFF_X, xp);
-      if constexpr (UPD) {
-        double dx[L::Ep];
+    if constexpr (UPD) {
+      if (mine) {
+        double xp[L::Dp], dx[L::Ep], xn[L::Dp];
+        vec_load(myrow + L::OFF_X, xp);
         vec_load(myrow + L::OFF_FV, dx);
-        double xn[L::Dp];
         M::err_fun(xp, dx, a.gv, xn);
         if constexpr (L::Dp > D) xn[L::Dp - 1] = 0.0;
         vec_store(myrow + L::OFF_X, xn);
         if ((a.flags & FLAG_NORM_AFTER_UPDATE) && a.n_quat > 0) lane_normalize(myrow + L::OFF_X, a);
-        vec_load(myrow + L::OFF_X, xp);
       }
-      if (o == n_obs - 1) {
-#pragma unroll
-        for (int i = 0; i < D; ++i) a.x[bl * D + i] = xp[i];
-        if (UPD && a.hx_filt) {
-#pragma unroll
-          for (int i = 0; i < D; ++i) a.hx_filt[bl * D + i] = xp[i];
-        }
-      }
+      __syncwarp();
+    }
+    if (o == n_obs - 1) {
+      stage_out<D, RS>(a.x + b0 * D, s.rows, L::OFF_X, ng, lane);
+      if (UPD && a.hx_filt) stage_out<D, RS>(a.hx_filt + b0 * D, s.rows, L::OFF_X, ng, lane);
     }
     __syncwarp();
+  }
+  if constexpr (TMA && RNB_TMA_STORE) {
+    if (lane == 0) tma_store_wait_read();  // shared memory must outlive the bulk stores reading it
   }
 }
 

@@ -163,7 +163,7 @@ def test_host_buffer_entry_point_equals_device_path(gen_dir):
   qi = ffi.new("int[]", [3])
   p = lambda a: ffi.cast("double *", a.ctypes.data)
   lib.live_host_step_12(p(hx), p(hP), ffi.cast("const double *", Qm.ctypes.data), ffi.NULL, 0.01, p(hz),
-                        ffi.cast("const double *", R.ctypes.data), ffi.NULL, 1, B, qi, 1, 3)
+                        ffi.cast("const double *", R.ctypes.data), ffi.NULL, 1, B, qi, 1, e.flags)
   assert lib.live_cuda_status() == 0
   assert np.array_equal(hx, e.state()) and np.array_equal(hP, e.covs()) and np.array_equal(hz, y)
 
