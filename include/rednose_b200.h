@@ -15,6 +15,7 @@
  *     void <name>_set_<var>(double);                                                          ekf_sym.py:166-171
  *   batched additions, DEVICE pointers, B independent filters, AoS row-major float64
  *     void <name>_batch_predict(...), <name>_batch_update_<kind>(...), <name>_batch_step_<kind>(...)
+ *     void <name>_batch_rts(...)   RTS smoother over a time-major history [T, B, ...]  (ekf_sym.py:651-690)
  *   batched, HOST pointers (copies inside): <name>_host_step_<kind>(...)
  *
  * All functions return void like the reference; CUDA failures are printed to stderr and
@@ -46,6 +47,8 @@ typedef void (*rednose_batch_update_fn)(double *x, double *P, double *z, const d
 typedef void (*rednose_batch_step_fn)(double *x, double *P, const double *Q, const double *dt_arr, double dt, double *z, const double *R, const double *ea, int n_obs, long long B, const int *quat_idxs, int n_quat, int flags, double *hx_pred, double *hP_pred, double *hx_filt, double *hP_filt, void *stream);
 typedef void (*rednose_host_step_fn)(double *x, double *P, const double *Q, const double *dt_arr, double dt, double *z, const double *R, const double *ea, int n_obs, long long B, const int *quat_idxs, int n_quat, int flags);
 
+typedef void (*rednose_batch_rts_fn)(const double *hx_pred, const double *hP_pred, const double *hx_filt, const double *hP_filt, const double *t, int t_per_filter, double *xs, double *Ps, int T, long long B, const int *quat_idxs, int n_quat, int norm_quats, void *stream);
+
 /* Plugin descriptor: replaces `struct EKF` (ekf.h:16-33).  Arrays have n_kinds entries,
  * parallel to `kinds`. */
 typedef struct rednose_ekf_desc {
@@ -74,6 +77,7 @@ typedef struct rednose_ekf_desc {
   const rednose_batch_update_fn *batch_updates;
   const rednose_batch_step_fn *batch_steps;
   const rednose_host_step_fn *host_steps;
+  rednose_batch_rts_fn batch_rts;   /* backward smoother over a stored history (ekf_sym.py:651-690) */
 } rednose_ekf_desc;
 
 /* ---- registry (librednose_b200.so; ekf_load.cc:4-39) ---- */

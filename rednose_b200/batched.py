@@ -156,3 +156,57 @@ class BatchedEKF:
     self.x.copy_(_as_device(x, self.device).expand_as(self.x))
     self.P.copy_(_as_device(P, self.device).expand_as(self.P))
     self.filter_time = filter_time
+
+  # ------------------------------------------------------- history + smoothing ---
+  def new_history(self, T):
+    """Device slabs for a T-step history, time-major: what the reference keeps as the list of
+    9-tuples returned by predict_and_update_batch (ekf_sym.py:531): x_{k|k-1}, x_{k|k}, P_{k|k-1}, P_{k|k}, t."""
+    return History(T, self.B, self.dim_x, self.dim_err, self.device)
+
+  def step_recorded(self, hist, kind, t, z, R, ea=None):
+    """predict_and_update_batch that also appends this step to `hist` (the kernel writes the slabs itself)."""
+    k = hist.n
+    assert k < hist.T, "history is full"
+    if self.filter_time is None:
+      self.filter_time = t
+    dt = t - self.filter_time
+    y = self.step(kind, dt, z, R, ea, hist_pred=(hist.x_pred[k], hist.P_pred[k]), hist_filt=(hist.x_filt[k], hist.P_filt[k]))
+    self.filter_time = t
+    hist.t[k] = t
+    hist.n += 1
+    return y
+
+  def rts_smooth(self, hist, norm_quats=False, quaternion_idxs=(3,), in_place=False):
+    """Batched RTS backward pass over a recorded history (ekf_sym.py:651-690, one launch for all filters).
+
+    Returns (xs [T, B, DIM], Ps [T, B, EDIM, EDIM]) on the device.  `norm_quats` normalises the quaternion(s)
+    at `quaternion_idxs` the way the reference normalises its hard-coded slice 3:7.
+    """
+    T = hist.n
+    assert T >= 1
+    xs = hist.x_filt if in_place else torch.empty_like(hist.x_filt)
+    Ps = hist.P_filt if in_place else torch.empty_like(hist.P_filt)
+    qi = self._ffi.new("int[]", list(quaternion_idxs) or [0])
+    with torch.cuda.device(self.device):
+      getattr(self._lib, f"{self.name}_batch_rts")(
+        self._cp(hist.x_pred), self._cp(hist.P_pred), self._cp(hist.x_filt), self._cp(hist.P_filt), self._cp(hist.t), 0,
+        self._p(xs), self._p(Ps), T, self.B, qi, len(quaternion_idxs) if norm_quats else 0, 1 if norm_quats else 0, self._stream())
+    self.launches += 1
+    self._check("batch_rts")
+    return xs[:T], Ps[:T]
+
+
+class History:
+  """Time-major device buffers of a forward pass, consumed by the RTS kernel."""
+
+  def __init__(self, T, B, dim_x, dim_err, device):
+    kw = dict(dtype=torch.float64, device=device)
+    self.T, self.B, self.n = T, B, 0
+    self.x_pred = torch.empty(T, B, dim_x, **kw)
+    self.x_filt = torch.empty(T, B, dim_x, **kw)
+    self.P_pred = torch.empty(T, B, dim_err, dim_err, **kw)
+    self.P_filt = torch.empty(T, B, dim_err, dim_err, **kw)
+    self.t = torch.zeros(T, **kw)
+
+  def bytes(self):
+    return sum(t.numel() * 8 for t in (self.x_pred, self.x_filt, self.P_pred, self.P_filt, self.t))

@@ -10,6 +10,7 @@
 #include "ekf_thread.cuh"
 #include "ekf_warp.cuh"
 #include "ekf_cta.cuh"
+#include "ekf_rts.cuh"
 #include <cstring>
 #include <mutex>
 
@@ -115,6 +116,20 @@ inline void batch_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, c
   a.z = z; a.R = R; a.ea = (K::EADIM > 0) ? ea : nullptr; a.ea_dim = K::EADIM; a.n_obs = n_obs;
   a.hx_pred = hx_pred; a.hP_pred = hP_pred; a.hx_filt = hx_filt; a.hP_filt = hP_filt;
   launch_step<M, K, PRED, true>(a, (cudaStream_t)stream);
+}
+
+template <class M>
+inline void batch_rts(HostCtx<M>& ctx, const double* hx_pred, const double* hP_pred, const double* hx_filt, const double* hP_filt,
+                      const double* t, int t_per_filter, double* xs, double* Ps, int T, long long B,
+                      const int* quat_idxs, int n_quat, int norm_quats, void* stream) {
+  RtsArgs<M::NG> a;
+  memset(&a, 0, sizeof(a));
+  a.hx_pred = hx_pred; a.hP_pred = hP_pred; a.hx_filt = hx_filt; a.hP_filt = hP_filt;
+  a.t = t; a.t_per_filter = t_per_filter; a.xs = xs; a.Ps = Ps; a.T = T; a.B = B; a.norm_quats = norm_quats;
+  a.n_quat = n_quat < 0 ? 0 : (n_quat > MAX_QUAT ? MAX_QUAT : n_quat);
+  for (int i = 0; i < a.n_quat; ++i) a.quat_idx[i] = quat_idxs[i];
+  for (int i = 0; i < (M::NG > 0 ? M::NG : 1); ++i) a.gv[i] = ctx.gv.v[i];
+  launch_rts<M>(a, (cudaStream_t)stream);
 }
 
 // --------------------------------------------- batched, HOST buffers (stateless) ---

@@ -188,3 +188,45 @@ def test_full_size_properties_1m_live(gen_dir, oracle_dir):
   xr, Pr, yr = o.batch_step(4, x, P, Qm, 0.01, z, R, quat_idxs=[3], flags=3)
   assert rel_err(xs[-1].cpu().numpy(), xr) < TIGHT and rel_err(Ps[-1].cpu().numpy(), Pr) < TIGHT
   assert B == 1048576
+
+
+def _record_live_history(gen_dir, o, B, T, seed, well_conditioned=True):
+  x, P, Qm = live_batch(B, seed=seed, well_conditioned=well_conditioned)
+  e = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  hist = e.new_history(T)
+  xr = x.copy()
+  for k in range(T):
+    kind = 12 if k % 10 == 0 else (4 if k % 2 else 10)
+    z, R = live_obs(o, kind, e.state() if k else xr, seed=500 + k)
+    e.step_recorded(hist, kind, 0.01 * (k + 1), z, R)
+  return e, hist
+
+
+@pytest.mark.parametrize("norm_quats", [False, True])
+def test_rts_smoother_matches_reference_recursion(gen_dir, oracle_dir, norm_quats):
+  """K2: the batched backward kernel vs the restated ekf_sym.py:651-690 on the SAME recorded history."""
+  from oracle.rts_numpy import rts_smooth
+  o = Oracle(oracle_dir, "live")
+  B, T = 33, 40
+  e, hist = _record_live_history(gen_dir, o, B, T, seed=61)
+  hx_p, hx_f = hist.x_pred.cpu().numpy(), hist.x_filt.cpu().numpy()
+  hP_p, hP_f = hist.P_pred.cpu().numpy(), hist.P_filt.cpu().numpy()
+  t = hist.t.cpu().numpy()
+  xs, Ps = e.rts_smooth(hist, norm_quats=norm_quats)
+  xs, Ps = xs.cpu().numpy(), Ps.cpu().numpy()
+  worst_x = worst_P = 0.0
+  for b in range(0, B, 4):
+    xr, Pr = rts_smooth(o, hx_p[:, b], hx_f[:, b], hP_p[:, b], hP_f[:, b], t, 23, 22, norm_quats=norm_quats)
+    worst_x = max(worst_x, rel_err(xs[:, b], xr))
+    worst_P = max(worst_P, rel_err(Ps[:, b], Pr))
+  assert worst_x < TOL and worst_P < TOL, (worst_x, worst_P)
+  # smoothing must not increase the position variance of interior points
+  assert np.all(Ps[5, :, 0, 0] <= hP_f[5, :, 0, 0] * (1 + 1e-9))
+
+
+def test_history_slabs_equal_separate_predict_update(gen_dir, oracle_dir):
+  o = Oracle(oracle_dir, "live")
+  e, hist = _record_live_history(gen_dir, o, 17, 3, seed=71)
+  # the last filtered slab is the live state; the predicted slab differs from it
+  assert torch.equal(hist.x_filt[2], e.x) and torch.equal(hist.P_filt[2], e.P)
+  assert not torch.equal(hist.P_pred[2], e.P)
