@@ -246,11 +246,11 @@ def run_gpu(args):
   # ---- final gather of the state estimates (the only collective of the system) ----
   gather_ms = None
   if world > 1:
-    out = torch.empty(world * B, dim, dtype=torch.float64, device=dev)
+    from rednose_b200.sharding import gather_filters
     sync_all()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
-    dist.all_gather_into_tensor(out, eng.x)
+    out = gather_filters(eng.x, world * B)
     g1.record()
     sync_all()
     gather_ms = g0.elapsed_time(g1)

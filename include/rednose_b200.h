@@ -86,6 +86,27 @@ const rednose_ekf_desc *rednose_b200_lookup(const char *name);
 /* dlopen(<dir>/lib<name>.so) + ekf_get() + register; returns 0 on success */
 int rednose_b200_load_and_register(const char *directory, const char *name);
 
+/* ---- native single-filter driver (librednose_b200.so; rednose/helpers/ekf_sym.{h,cc} EKFSym) ----
+ * The handle owns x, P, Q, the filter time (NaN = unset, ekf_sym.cc:42) and the rewind ring (512 checkpoints,
+ * ekf_sym.h:18).  All numerics go through the filter library's <name>_predict / <name>_update_<kind>. */
+void *rednose_ekfsym_create(const char *directory, const char *name, const double *Q, const double *x0, const double *P0, int dim_x, int dim_err, int dim_main, int dim_main_err, int N, int dim_augment, int dim_augment_err, const int *maha_test_kinds, int n_maha, const int *quaternion_idxs, int n_quat, double max_rewind_age);
+void rednose_ekfsym_destroy(void *h);
+void rednose_ekfsym_init_state(void *h, const double *x, const double *P, double filter_time);
+double *rednose_ekfsym_x_ptr(void *h);   /* live views, valid until destroy / init_state */
+double *rednose_ekfsym_P_ptr(void *h);
+double rednose_ekfsym_get_filter_time(void *h);
+void rednose_ekfsym_set_filter_time(void *h, double t);
+void rednose_ekfsym_reset_rewind(void *h);
+int rednose_ekfsym_rewind_depth(void *h);
+void rednose_ekfsym_normalize_quaternions(void *h);
+void rednose_ekfsym_augment(void *h);                                /* ekf_sym.py:365-391 */
+void rednose_ekfsym_get_augment_times(void *h, double *out);
+int rednose_ekfsym_set_global(void *h, const char *var, double val); /* 0 = ok, -1 = unknown variable */
+void *rednose_ekfsym_get_extra_routine(void *h, const char *routine);
+void rednose_ekfsym_predict(void *h, double t);                      /* ekf_sym.cc:196-209 */
+/* ekf_sym.cc:83-117: returns 1 (outputs filled), 0 (observation too old, ignored), -1 (unknown kind) */
+int rednose_ekfsym_predict_and_update_batch(void *h, double t, int kind, const double *z, const double *R, const double *ea, int n, int zdim, int eadim, int augment, double *xk1, double *xk, double *Pk1, double *Pk, double *y);
+
 #ifdef __cplusplus
 }
 /* self-registration used by generated libraries (ekf.h:39-42): only if the registry is linked in */

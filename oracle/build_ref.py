@@ -79,7 +79,28 @@ def assemble(name, gen_dir):
   with open(os.path.join(HERE, "batch_runner.inc"), encoding="utf-8") as f:
     runner = f.read()
   dispatch = "\n".join(f"    case {k}: {name}_update_{k}(x, P, z, R, ea); break;" for k in kinds)
-  runner = runner.replace("@NAME@", name).replace("@DISPATCH@", dispatch)
+  import re
+  upd = re.findall(r"void " + name + r"_update_(\d+)\(double \*in_x.*?\{\s*update<(\d+), 3, (\d)>\(in_x, in_P, h_\d+, H_\d+, (\w+),", post, flags=re.S)
+  dims = {k: int(re.search(r"#define " + k + r" (\d+)", head).group(1)) for k in ("DIM", "EDIM", "MEDIM")}
+  kl = [int(u[0]) for u in upd]
+  desc = ["", "// plugin descriptor over the CPU functions, so the native driver (runtime.cc) can be tested without a GPU",
+          f'#include "{os.path.join(REPO, "include", "rednose_b200.h")}"',
+          "namespace {",
+          f"const int okinds_[] = {{ {', '.join(map(str, kl))} }};",
+          f"const int ozdims_[] = {{ {', '.join(u[1] for u in upd)} }};",
+          f"const int oeadims_[] = {{ {', '.join('3' if u[3] != 'NULL' else '0' for u in upd)} }};",
+          f"const int ofeat_[] = {{ {', '.join('1' if u[3] != 'NULL' else '0' for u in upd)} }};",
+          f"const int omaha_[] = {{ {', '.join(u[2] for u in upd)} }};",
+          f"const rednose_leaf3_fn ohs_[] = {{ {', '.join(f'{name}_h_{k}' for k in kl)} }};",
+          f"const rednose_leaf3_fn oHs_[] = {{ {', '.join(f'{name}_H_{k}' for k in kl)} }};",
+          f"const rednose_leaf3_fn oHes_[] = {{ {', '.join((f'{name}_He_{u[0]}' if u[3] != 'NULL' else 'nullptr') for u in upd)} }};",
+          f"const rednose_update_fn oupd_[] = {{ {', '.join(f'{name}_update_{k}' for k in kl)} }};",
+          "const char* const onone_[] = { nullptr }; const rednose_set_fn osets_[] = { nullptr }; void* const oext_[] = { nullptr };",
+          f'const rednose_ekf_desc odesc_ = {{ 1, "{name}", {dims["DIM"]}, {dims["EDIM"]}, {dims["MEDIM"]}, {len(kl)}, okinds_, ozdims_, oeadims_, ofeat_, omaha_,',
+          f"  {name}_f_fun, {name}_F_fun, {name}_err_fun, {name}_inv_err_fun, {name}_H_mod_fun, {name}_predict, ohs_, oHs_, oHes_, oupd_,",
+          "  0, onone_, osets_, 0, onone_, oext_, nullptr, nullptr, nullptr, nullptr, nullptr };",
+          "}", 'extern "C" void* ekf_get() { return (void*)&odesc_; }', ""]
+  runner = runner.replace("@NAME@", name).replace("@DISPATCH@", dispatch) + "\n".join(desc)
   tu = (f"// assembled by oracle/build_ref.py from the reference generator's output -- not committed\n"
         f"#include <math.h>\n#include <string.h>\n#include <stddef.h>\n#include <vector>\n#include <thread>\n#include <cmath>\n{head}\n"
         f"#include \"{os.path.join(HERE, 'ekf_oracle_core.h')}\"\n{post}\n{runner}\n")

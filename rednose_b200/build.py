@@ -35,7 +35,8 @@ def _newer(target, sources):
 
 
 def csrc_sources():
-  return [os.path.join(CSRC_DIR, f) for f in sorted(os.listdir(CSRC_DIR))] + [os.path.join(INCLUDE_DIR, "rednose_b200.h")]
+  # what a generated filter library depends on (the runtime library is built separately)
+  return [os.path.join(CSRC_DIR, f) for f in sorted(os.listdir(CSRC_DIR)) if f != "runtime.cc"] + [os.path.join(INCLUDE_DIR, "rednose_b200.h")]
 
 
 def compile_filter(folder, name, force=False, verbose=False):
@@ -62,7 +63,7 @@ def compile_runtime(force=False):
   """csrc/runtime.cc -> rednose_b200/librednose_b200.so (registry + native driver)."""
   src = os.path.join(CSRC_DIR, "runtime.cc")
   lib = os.path.join(PKG_DIR, "librednose_b200.so")
-  if not force and _newer(lib, [src] + csrc_sources()):
+  if not force and _newer(lib, [src, os.path.join(INCLUDE_DIR, "rednose_b200.h")]):
     return lib
   cxx = shutil.which("g++") or "g++"
   cmd = [cxx, "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", f"-I{INCLUDE_DIR}", "-o", lib, src, "-ldl"]

@@ -1,0 +1,44 @@
+"""Multi-GPU layout of a batch of independent filters.
+
+Filters never interact (no cross-filter term anywhere in ekf_c.c / ekf_sym.cc), so the batch is cut into
+contiguous shards, one per rank / GPU; stepping and smoothing need NO communication.  The only collective
+of the system is the optional final gather of the state estimates (and, if asked, covariances) over
+NCCL / NVLink.  One process per GPU, `torch.distributed` for the plumbing.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total: int, rank: int, world: int) -> tuple[int, int]:
+  """Contiguous [lo, hi) of `total` filters owned by `rank`; sizes differ by at most one."""
+  base, rem = divmod(total, world)
+  lo = rank * base + min(rank, rem)
+  return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(total: int, world: int) -> list[int]:
+  return [shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0] for r in range(world)]
+
+
+def gather_filters(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
+  """All-gather per-filter rows ([B_local, ...]) of every rank into [total, ...] in rank order.
+
+  Shards may be ragged (total not divisible by world): rows are padded to the largest shard for the
+  collective and trimmed afterwards.
+  """
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return local
+  world = dist.get_world_size(group)
+  sizes = shard_sizes(total, world)
+  assert local.shape[0] == sizes[dist.get_rank(group)]
+  pad = max(sizes)
+  buf = local
+  if local.shape[0] < pad:
+    buf = torch.cat([local, local.new_zeros((pad - local.shape[0],) + tuple(local.shape[1:]))])
+  out = local.new_empty((world * pad,) + tuple(local.shape[1:]))
+  dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
+  if all(s == pad for s in sizes):
+    return out
+  return torch.cat([out[r * pad:r * pad + sizes[r]] for r in range(world)])
