@@ -22,7 +22,7 @@ class Oracle:
   def p(self, a):
     return self.ffi.cast("double *", a.ctypes.data) if a is not None else self.ffi.NULL
 
-  def batch_step(self, kind, x, P, Q, dt, z, R, ea=None, quat_idxs=(), flags=0, nthreads=8):
+  def batch_step(self, kind, x, P, Q, dt, z, R, ea=None, quat_idxs=(), flags=0, nthreads=8):  # noqa: E501
     """In place on copies; returns (x, P, y)."""
     x, P, z, R = (np.array(a, dtype=np.float64, order='C') for a in (x, P, z, R))
     Q = np.ascontiguousarray(Q, dtype=np.float64)

@@ -157,6 +157,13 @@ class BatchedEKF:
     self.P.copy_(_as_device(P, self.device).expand_as(self.P))
     self.filter_time = filter_time
 
+  def augment(self):
+    """MSCKF clone window shift for the whole batch (ekf_sym.py:365-391), one launch."""
+    with torch.cuda.device(self.device):
+      getattr(self._lib, f"{self.name}_batch_augment")(self._p(self.x), self._p(self.P), self.B, self._stream())
+    self.launches += 1
+    self._check("batch_augment")
+
   # ------------------------------------------------------- history + smoothing ---
   def new_history(self, T):
     """Device slabs for a T-step history, time-major: what the reference keeps as the list of

@@ -11,6 +11,7 @@
 #include "ekf_warp.cuh"
 #include "ekf_cta.cuh"
 #include "ekf_rts.cuh"
+#include "ekf_augment.cuh"
 #include <cstring>
 #include <mutex>
 

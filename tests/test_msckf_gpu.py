@@ -1,0 +1,103 @@
+"""GPU parity tests of the CTA-per-filter path (EDIM 82): synthetic MSCKF with 10 cloned poses, feature-track
+updates with left-null-space projection and Mahalanobis gating, state augmentation."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import Oracle, live_obs, msckf_batch, msckf_feature_obs, rel_err
+
+pytestmark = pytest.mark.gpu
+QUATS = [3] + [23 + 3 + 7 * c for c in range(10)]
+
+
+@pytest.fixture(scope="module")
+def msckf_dirs(gen_dir, oracle_dir):
+  import os
+  from oracle import build_ref
+  from rednose_b200.filters import ensure_generated
+  from rednose_b200.filters.msckf import MsckfKalman
+  ensure_generated(MsckfKalman)
+  if build_ref.reference_available():
+    build_ref.build("msckf", "rednose_b200.filters.msckf:MsckfKalman")
+  if not os.path.exists(os.path.join(build_ref.OUT, "libmsckf.so")):
+    pytest.skip("oracle/_ref/libmsckf.so not built")
+  return gen_dir, oracle_dir
+
+
+def _engine(gen_dir, x, P, Q, **kw):
+  from rednose_b200.batched import BatchedEKF
+  return BatchedEKF(gen_dir, "msckf", Q, x, P, quaternion_idxs=QUATS, **kw)
+
+
+def test_msckf_predict_block_structure(msckf_dirs):
+  gen_dir, oracle_dir = msckf_dirs
+  o = Oracle(oracle_dir, "msckf")
+  x, P, Q, _ = msckf_batch(37, seed=1)
+  xr, Pr = o.predict(x, P, Q, 0.05)
+  e = _engine(gen_dir, x, P, Q, norm_after_predict=False, norm_after_update=False)
+  e.predict(0.05)
+  assert rel_err(e.state(), xr) < 1e-12 and rel_err(e.covs(), Pr) < 1e-9
+  # clones are static: their block of P is untouched by the predict (ekf_c.c:23-26)
+  assert np.array_equal(e.covs()[:, 22:, 22:], P[:, 22:, 22:])
+
+
+def test_msckf_plain_kind_on_the_big_state(msckf_dirs):
+  gen_dir, oracle_dir = msckf_dirs
+  o, ol = Oracle(oracle_dir, "msckf"), Oracle(oracle_dir, "live")
+  x, P, Q, _ = msckf_batch(41, seed=2)
+  z, R = live_obs(ol, 12, x[:, :23])
+  xr, Pr, yr = o.batch_step(12, x, P, Q, 0.01, z, R, quat_idxs=QUATS, flags=3)
+  e = _engine(gen_dir, x, P, Q)
+  y = e.step(12, 0.01, z, R)
+  assert rel_err(e.state(), xr) < 1e-9 and rel_err(e.covs(), Pr) < 1e-8 and rel_err(y.cpu().numpy()[:, 0], yr) < 1e-9
+
+
+@pytest.mark.parametrize("outlier_frac", [0.0, 0.3])
+def test_msckf_feature_update_nullspace_and_gate(msckf_dirs, outlier_frac):
+  """x and P are invariant to the null-space basis (ekf_c.c:71 fullPivLu().kernel() vs Householder here);
+  the returned innovation is basis dependent and only its norm is compared."""
+  gen_dir, oracle_dir = msckf_dirs
+  o = Oracle(oracle_dir, "msckf")
+  B = 48
+  x, P, Q, point = msckf_batch(B, seed=3)
+  z, R, out = msckf_feature_obs(o, x, point, seed=4, outlier_frac=outlier_frac)
+  xr, Pr, yr = o.update(17, x, P, z, R, ea=point)
+  e = _engine(gen_dir, x, P, Q, norm_after_update=False)
+  y = e.update(17, z, R, ea=point).cpu().numpy()[:, 0]
+  ex, eP = rel_err(e.state(), xr), rel_err(e.covs(), Pr)
+  assert ex < 1e-9 and eP < 1e-7, (ex, eP)
+  if outlier_frac:
+    # gated filters keep (essentially) their prior covariance; the others shrink it
+    shrink = np.trace(e.covs(), axis1=1, axis2=2) / np.trace(P, axis1=1, axis2=2)
+    gated = shrink > 1 - 1e-9
+    assert gated.any() and (~gated).any() and np.all(out[gated])   # the gate fired, and only on gross outliers
+
+
+def test_msckf_fused_step_with_feature_kind(msckf_dirs):
+  gen_dir, oracle_dir = msckf_dirs
+  o = Oracle(oracle_dir, "msckf")
+  B = 33
+  x, P, Q, point = msckf_batch(B, seed=5)
+  xp, _ = o.predict(x, P, Q, 0.01)
+  z, R, _ = msckf_feature_obs(o, xp, point, seed=6)
+  xr, Pr, _ = o.batch_step(17, x, P, Q, 0.01, z, R, ea=point, quat_idxs=QUATS, flags=3)
+  e = _engine(gen_dir, x, P, Q)
+  e.step(17, 0.01, z, R, ea=point)
+  assert rel_err(e.state(), xr) < 1e-9 and rel_err(e.covs(), Pr) < 1e-7
+
+
+def test_batched_augment_equals_reference_selection(msckf_dirs):
+  """K3 vs the selection-matrix formulation of ekf_sym.py:365-391 written out in numpy."""
+  gen_dir, _ = msckf_dirs
+  x, P, Q, _ = msckf_batch(19, seed=7)
+  e = _engine(gen_dir, x, P, Q)
+  e.augment()
+  d1, d2, d3, d4, n = 23, 22, 7, 6, 82
+  xr = x.copy()
+  xr[:, d1:-d3] = x[:, d1 + d3:]
+  xr[:, -d3:] = x[:, :d3]
+  to_mult = np.zeros((n, n - d4))
+  to_mult[:-d4, :] = np.eye(n - d4)
+  to_mult[-d4:, :d4] = np.eye(d4)
+  Pr = np.stack([to_mult @ np.delete(np.delete(Pb, np.s_[d2:d2 + d4], axis=1), np.s_[d2:d2 + d4], axis=0) @ to_mult.T for Pb in P])
+  assert np.array_equal(e.state(), xr) and np.array_equal(e.covs(), Pr)

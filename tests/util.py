@@ -65,3 +65,44 @@ def kinematic_batch(B, seed=0):
   z = x[:, :1] + rng.normal(0, 0.1, (B, 1))
   R = np.tile(np.array([[0.1**2]]), (B, 1, 1))
   return x, P, KinematicKalman.Q.copy(), z, R
+
+
+def msckf_batch(B, seed=0, outlier_frac=0.0):
+  """Synthetic MSCKF states: live main state, 10 clones = the main pose displaced along a short track,
+  one 3-D point 10-50 m ahead seen from every clone."""
+  from rednose_b200.filters.msckf import DIM, DIM_AUGMENT, EDIM, N_CLONES, MsckfKalman
+  from rednose_b200.filters.live import DIM_STATE
+  from rednose_b200.geometry import quat2rot
+  rng = np.random.default_rng(seed)
+  xm, _, _ = live_batch(B, seed=seed)
+  x = np.zeros((B, DIM))
+  x[:, :DIM_STATE] = xm
+  Rm = quat2rot(xm[:, 3:7])                       # device -> ecef
+  fwd = Rm[:, :, 0]
+  for c in range(N_CLONES):
+    o = DIM_STATE + c * DIM_AUGMENT
+    x[:, o:o + 3] = xm[:, 0:3] - fwd * 0.5 * (N_CLONES - c) + rng.normal(0, 0.02, (B, 3))
+    q = xm[:, 3:7] + rng.normal(0, 0.002, (B, 4))
+    x[:, o + 3:o + 7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+  s = np.sqrt(np.concatenate([[25.0] * 3 + [0.05**2] * 3 + [1.0] * 3 + [0.1**2] * 3 + [0.01**2] * 3 + [0.01**2] + [0.5**2] * 3 + [0.01**2] * 3]
+                             + [[1.0] * 3 + [0.02**2] * 3] * N_CLONES))
+  L = np.eye(EDIM)[None] + 0.05 * np.tril(rng.normal(size=(B, EDIM, EDIM)), -1)
+  L = s[None, :, None] * L
+  P = L @ np.transpose(L, (0, 2, 1))
+  P = 0.5 * (P + np.transpose(P, (0, 2, 1)))
+  local = np.stack([rng.uniform(10, 50, B), rng.uniform(-5, 5, B), rng.uniform(-3, 3, B)], 1)
+  point = xm[:, 0:3] + np.einsum('bij,bj->bi', Rm, local)
+  return x, P, MsckfKalman.Q.copy(), point
+
+
+def msckf_feature_obs(oracle, x, point, seed=1, sigma=1e-3, outlier_frac=0.0):
+  rng = np.random.default_rng(seed)
+  B = x.shape[0]
+  z = np.zeros((B, 20))
+  for b in range(B):
+    oracle.leaf("h_17", np.ascontiguousarray(x[b]), np.ascontiguousarray(point[b]), z[b])
+  noise = rng.normal(0, sigma, (B, 20))
+  out = rng.random(B) < outlier_frac
+  noise[out] *= 50.0
+  R = np.tile(np.eye(20) * sigma**2, (B, 1, 1))
+  return z + noise, R, out
