@@ -35,6 +35,7 @@ extern "C" {
 #define REDNOSE_NORM_AFTER_PREDICT 1
 #define REDNOSE_NORM_AFTER_UPDATE 2
 #define REDNOSE_Q_IS_DIAGONAL 4      /* caller promises Q is diagonal: kernels read only its diagonal */
+#define REDNOSE_SHARED_R 8           /* R is one [ZDIM, ZDIM] matrix shared by the whole batch (what get_R builds, kalmanfilter.py:37-43) */
 
 typedef void (*rednose_leaf3_fn)(double *, double *, double *);
 typedef void (*rednose_leaf2_fn)(double *, double *);

@@ -19,6 +19,7 @@ from rednose_b200.loader import load_code, raise_on_cuda_error
 NORM_AFTER_PREDICT = 1
 NORM_AFTER_UPDATE = 2
 Q_IS_DIAGONAL = 4
+SHARED_R = 8
 
 
 def _as_device(t, device, dtype=torch.float64):
@@ -100,20 +101,26 @@ class BatchedEKF:
     R = _as_device(R, self.device)
     if z.ndim == 2:
       z = z.unsqueeze(1)
-    if R.ndim == 3:
-      R = R.unsqueeze(1)
-    assert z.shape[0] == self.B and R.shape[:2] == z.shape[:2] and R.shape[2] == R.shape[3] == z.shape[2]
+    flags = self.flags
+    if R.ndim == 2:   # one noise matrix for the whole batch (what KalmanFilter.get_R replicates, kalmanfilter.py:37-43)
+      assert R.shape[0] == R.shape[1] == z.shape[2]
+      flags |= SHARED_R
+    else:
+      if R.ndim == 3:
+        R = R.unsqueeze(1)
+      assert R.shape[:2] == z.shape[:2] and R.shape[2] == R.shape[3] == z.shape[2]
+    assert z.shape[0] == self.B
     ea = _as_device(ea, self.device) if ea is not None else None
-    return z, R, ea, z.shape[1]
+    return z, R, ea, z.shape[1], flags
 
   def update(self, kind, z, R, ea=None, hist=None):
     """Measurement update of one kind for the whole batch (ekf_c.c:37-121); returns the innovations y [B, n, m]."""
-    z, R, ea, n_obs = self._obs_args(z, R, ea)
+    z, R, ea, n_obs, flags = self._obs_args(z, R, ea)
     hx, hP = (hist if hist is not None else (None, None))
     with torch.cuda.device(self.device):
       getattr(self._lib, f"{self.name}_batch_update_{kind}")(
         self._p(self.x), self._p(self.P), self._p(z), self._cp(R), self._cp(ea), n_obs, self.B,
-        self._quat, self._nquat, self.flags, self._p(hx), self._p(hP), self._stream())
+        self._quat, self._nquat, flags, self._p(hx), self._p(hP), self._stream())
     self.launches += 1
     self._check(f"batch_update_{kind}")
     return z
@@ -121,13 +128,13 @@ class BatchedEKF:
   def step(self, kind, dt, z, R, ea=None, hist_pred=None, hist_filt=None):
     """Fused predict(dt) + update(kind): one kernel launch, P read and written once."""
     keep, dt_ptr, dt_s = self._dt_args(dt)
-    z, R, ea, n_obs = self._obs_args(z, R, ea)
+    z, R, ea, n_obs, flags = self._obs_args(z, R, ea)
     hxp, hPp = (hist_pred if hist_pred is not None else (None, None))
     hxf, hPf = (hist_filt if hist_filt is not None else (None, None))
     with torch.cuda.device(self.device):
       getattr(self._lib, f"{self.name}_batch_step_{kind}")(
         self._p(self.x), self._p(self.P), self._cp(self.Q), dt_ptr, dt_s, self._p(z), self._cp(R), self._cp(ea),
-        n_obs, self.B, self._quat, self._nquat, self.flags, self._p(hxp), self._p(hPp), self._p(hxf), self._p(hPf),
+        n_obs, self.B, self._quat, self._nquat, flags, self._p(hxp), self._p(hPp), self._p(hxf), self._p(hPf),
         self._stream())
     self.launches += 1
     self._check(f"batch_step_{kind}")

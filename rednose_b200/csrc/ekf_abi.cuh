@@ -181,7 +181,8 @@ inline void host_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, co
     cudaMemcpyAsync(dP, P + b0 * E * E, sizeof(double) * nb * E * E, cudaMemcpyHostToDevice, st);
     if (dt_arr) cudaMemcpyAsync(ddt, dt_arr + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(dz, z + b0 * n_obs * Z, sizeof(double) * nb * n_obs * Z, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dR, R + b0 * n_obs * Z * Z, sizeof(double) * nb * n_obs * Z * Z, cudaMemcpyHostToDevice, st);
+    if (flags & FLAG_SHARED_R) cudaMemcpyAsync(dR, R, sizeof(double) * Z * Z, cudaMemcpyHostToDevice, st);
+    else cudaMemcpyAsync(dR, R + b0 * n_obs * Z * Z, sizeof(double) * nb * n_obs * Z * Z, cudaMemcpyHostToDevice, st);
     if (EA > 0 && ea) cudaMemcpyAsync(dea, ea + b0 * n_obs * EA, sizeof(double) * nb * n_obs * EA, cudaMemcpyHostToDevice, st);
     StepArgs<M::NG> a;
     fill_common<M>(a, ctx, nb, quat_idxs, n_quat, flags);

@@ -18,6 +18,7 @@ enum : int {
   FLAG_NORM_AFTER_PREDICT = 1,  // ekf_sym.cc:207 (the C++ driver does, the python driver does not)
   FLAG_NORM_AFTER_UPDATE  = 2,  // ekf_sym.cc:213 / ekf_sym.py:521
   FLAG_Q_DIAG             = 4,  // caller promises Q is diagonal (only its diagonal is read)
+  FLAG_SHARED_R           = 8,  // R points at ONE [ZDIM, ZDIM] matrix used by every filter / observation
 };
 
 // One argument block per launch, passed by value (lives in the kernel parameter

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(((M::EDIM + 31) / 32) * 32) ekf_step_cta(const
     for (int i = tid; i < (K::NH > 0 ? K::NH : 1); i += nth) s.hv[i] = ws[W::OFF_HV + i];
     for (int i = tid; i < Z; i += nth) s.y[i] = ws[W::OFF_Y + i];
     if constexpr (K::HAS_HE) for (int i = tid; i < Z * K::EADIM; i += nth) s.He[i] = ws[W::OFF_HE + i];
-    const double* Rg = a.R + (b * a.n_obs + o) * (long long)(Z * Z);
+    const double* Rg = a.R + ((a.flags & FLAG_SHARED_R) ? 0 : (b * a.n_obs + o) * (long long)(Z * Z));
     for (int idx = tid; idx < Z * Z; idx += nth) s.Rm[(idx / Z) * SL + idx % Z] = Rg[idx];
     if (tid == 0) s.gated = 0;
   }

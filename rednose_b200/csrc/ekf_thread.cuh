@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) ekf_step_thread(const StepArgs<M::NG> a) 
 #pragma unroll
       for (int i = 0; i < Z; ++i)
 #pragma unroll
-        for (int j = 0; j < Z; ++j) R[i][j] = a.R[bo * Z * Z + i * Z + j];
+        for (int j = 0; j < Z; ++j) R[i][j] = a.R[((a.flags & FLAG_SHARED_R) ? 0 : bo * Z * Z) + i * Z + j];
       const double* ea = a.ea ? a.ea + bo * a.ea_dim : nullptr;
 
       double hx[Z];

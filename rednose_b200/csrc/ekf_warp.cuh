@@ -211,15 +211,22 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
     // ---- stage this group's small per-filter records into the rows (coalesced) ----
     if (o == 0) stage_in<D, RS>(a.x + b0 * D, s.rows, L::OFF_X, ng, lane);
     if constexpr (UPD) {
+      const bool shared_R = a.flags & FLAG_SHARED_R;
       if (a.n_obs == 1) {
         stage_in<Z, RS>(a.z + b0 * Z, s.rows, L::OFF_Y, ng, lane);
-        stage_in<Z * Z, RS>(a.R + b0 * (Z * Z), s.rows, L::OFF_R, ng, lane);
+        if (!shared_R) stage_in<Z * Z, RS>(a.R + b0 * (Z * Z), s.rows, L::OFF_R, ng, lane);
       } else if (mine) {
         const long long bo = (b0 + lane) * a.n_obs + o;
 #pragma unroll
         for (int i = 0; i < Z; ++i) myrow[L::OFF_Y + i] = a.z[bo * Z + i];
+        if (!shared_R) {
 #pragma unroll
-        for (int i = 0; i < Z * Z; ++i) myrow[L::OFF_R + i] = a.R[bo * (Z * Z) + i];
+          for (int i = 0; i < Z * Z; ++i) myrow[L::OFF_R + i] = a.R[bo * (Z * Z) + i];
+        }
+      }
+      if (shared_R && mine) {
+#pragma unroll
+        for (int i = 0; i < Z * Z; ++i) myrow[L::OFF_R + i] = __ldg(a.R + i);
       }
     }
     __syncwarp();

@@ -257,3 +257,43 @@ def test_cuda_path_reproduces_reference_golden_vectors(gen_dir):
   xs, Ps = e.rts_smooth(hist, norm_quats=True)
   for b in range(2):
     assert rel_err(xs[:, b].cpu().numpy(), g[f"xs{b}"]) < TOL and rel_err(Ps[:, b].cpu().numpy(), g[f"Ps{b}"]) < TOL
+
+
+def test_shared_R_equals_replicated_R(gen_dir):
+  B = 513
+  x, P, Qm = live_batch(B, seed=81)
+  rng = np.random.default_rng(1)
+  z = x[:, 0:3] + rng.normal(0, 5.0, (B, 3))
+  R1 = np.diag([25.0, 16.0, 9.0])
+  a = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  b = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  ya = a.step(12, 0.01, z, np.tile(R1, (B, 1, 1)))
+  yb = b.step(12, 0.01, z, R1)
+  assert torch.equal(a.x, b.x) and torch.equal(a.P, b.P) and torch.equal(ya, yb)
+
+
+def test_host_streamer_equals_direct_stepping(gen_dir):
+  """The overlapped host<->device front-end returns, for every step, exactly what direct stepping produces."""
+  from rednose_b200.streaming import HostStreamer
+  B, T = 4099, 7
+  x, P, Qm = live_batch(B, seed=91)
+  rng = np.random.default_rng(2)
+  R = {12: torch.as_tensor(np.diag([25.0] * 3)).cuda(), 4: torch.as_tensor(np.diag([0.025**2] * 3)).cuda()}
+  zs = [(12 if k % 3 == 0 else 4, torch.as_tensor((x[:, 0:3] if k % 3 == 0 else np.zeros((B, 3))) + rng.normal(0, 0.01, (B, 3))).pin_memory())
+        for k in range(T)]
+  a = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  b = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  st = HostStreamer(b, {12: 3, 4: 3})
+  a.filter_time = b.filter_time = 0.0
+  tickets, want = [], []
+  for k, (kind, z) in enumerate(zs):
+    t = 0.01 * (k + 1)
+    xa, ya = a.predict_and_update_batch(t, kind, z, R[kind])
+    want.append((xa.cpu().clone(), ya.cpu()[:, 0].clone()))
+    tickets.append(st.submit(t, kind, z, R[kind]))
+    if k >= 1:  # results of the previous step are still retrievable (depth 2)
+      xh, yh = st.result(tickets[k - 1], zs[k - 1][0])
+      assert torch.equal(xh, want[k - 1][0]) and torch.equal(yh, want[k - 1][1])
+  xh, yh = st.result(tickets[-1], zs[-1][0])
+  assert torch.equal(xh, want[-1][0]) and torch.equal(yh, want[-1][1])
+  assert torch.equal(a.P, b.P)
