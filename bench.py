@@ -34,6 +34,7 @@ WORKLOADS = {
   "live_1m": dict(filter="live", batch=1 << 20),
   "live_100k": dict(filter="live", batch=100_000),
   "kinematic_1m": dict(filter="kinematic", batch=1 << 20),
+  "kinematic_16m": dict(filter="kinematic", batch=1 << 24),   # 1.2 GB of state: larger than L2, a true HBM measurement
 }
 LIVE_R = {4: [0.025**2] * 3, 10: [0.5**2] * 3, 12: [5.0**2] * 3}
 L2_BYTES = 126 << 20
@@ -67,7 +68,7 @@ class ClockSampler:
 
   def __enter__(self):
     try:
-      self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+      self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
@@ -387,7 +388,7 @@ def run_reference(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=40)
+  ap.add_argument("--steps", type=int, default=200)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--workload", default="live_1m", choices=sorted(WORKLOADS))

@@ -32,7 +32,7 @@ namespace rnb {
 
 // tuning knobs (overridable at build time: -DRNB_GROUP=..., -DRNB_WARPS=...)
 #ifndef RNB_GROUP
-#define RNB_GROUP 8   // filters per warp group (leaf phase uses RNB_GROUP of the 32 lanes)
+#define RNB_GROUP 12  // filters per warp group (leaf phase uses RNB_GROUP of the 32 lanes)
 #endif
 #ifndef RNB_WARPS
 #define RNB_WARPS 1    // warps per CTA (warps never synchronise with each other)
@@ -42,7 +42,7 @@ namespace rnb {
 #define RNB_TMA 1      // stage covariance tiles through shared memory with cp.async.bulk (TMA) load + store
 #endif
 #ifndef RNB_STAGES
-#define RNB_STAGES 2   // covariance tile ring per warp = bulk loads in flight per warp
+#define RNB_STAGES 1   // covariance tile ring per warp = bulk loads in flight per warp
 #endif
 #ifndef RNB_TMA_STORE
 #define RNB_TMA_STORE 0  // 1: results leave through the tile with a bulk store; 0: plain coalesced stores from registers
@@ -121,7 +121,8 @@ struct WarpScratch {
   alignas(128) double tile[(NST > 0 ? NST : 1) * (use_tma<M>() ? M::EDIM * M::EDIM : 2)];  // covariance tiles (TMA ring)
   alignas(8) uint64_t full[NST > 0 ? NST : 1];                                              // "tile landed" mbarriers
   alignas(16) double rows[G * L::STRIDE];
-  alignas(16) double ex[(M::NFROWS > 0 ? M::NFROWS : 1) * 33];  // row exchange for F P F^T
+  static constexpr int EXS = 33;                                 // exchange row stride (odd: conflict-free column writes)
+  alignas(16) double ex[(M::NFROWS > 0 ? M::NFROWS : 1) * EXS];  // row exchange for F P F^T
   alignas(16) double hp[K::ZDIM * 32];                          // (H P)[c][k]
 };
 
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
   constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM;
   using L = RowLayout<M, K>;
   constexpr int RS = L::STRIDE;
+  constexpr int EXS = WarpScratch<M, K, G>::EXS;
   static_assert(E <= 32, "warp-per-filter kernel needs EDIM <= 32");
   static_assert(G <= 32, "group size");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -316,31 +318,28 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
         double fv[L::NFp];
         vec_load(row + L::OFF_FV, fv);
         const double dt = row[L::OFF_DT];
-        // m = F p (lane-local); rows of F P that are not rows of P go through the exchange
-        double m[E];
-#pragma unroll
-        for (int i = 0; i < E; ++i) m[i] = p[i];
-        M::F_apply(fv, m);
+        // rows of F P that are not rows of P (F's non-identity rows) go through the exchange; every other
+        // row j of F P equals column j of P (symmetry), which the lane already holds
         if constexpr (M::NFROWS > 0) {
-          M::frows_store(m, s.ex + lane, 33);
+          {
+            double m[E];
+#pragma unroll
+            for (int i = 0; i < E; ++i) m[i] = p[i];
+            M::F_apply(fv, m);                      // only the non-identity rows of m are computed / used
+            M::frows_store(m, s.ex + lane, EXS);
+          }
           __syncwarp();
           const bool in_rf = (M::FROW_MASK >> lane) & 1u;
           const int slot_rf = __popc(M::FROW_MASK & ((1u << lane) - 1u));
-          const double* xr = s.ex + slot_rf * 33;
-          double r[E];
+          if (in_rf) {  // this lane's row of F P replaces its column of P
+            const double* xr = s.ex + slot_rf * EXS;
 #pragma unroll
-          for (int i = 0; i < E; ++i) r[i] = m[i];
-          if (in_rf) {  // only the lanes owning a non-identity row of F read the exchange
-#pragma unroll
-            for (int i = 0; i < E; ++i) r[i] = xr[i];
+            for (int i = 0; i < E; ++i) p[i] = xr[i];
           }
-          M::F_apply(fv, r);
-#pragma unroll
-          for (int i = 0; i < E; ++i) p[i] = in_rf ? r[i] : m[i];
+          M::F_apply(fv, p);                        // column `lane` of F (F P)^T = F P F^T
           __syncwarp();
         } else {
-#pragma unroll
-          for (int i = 0; i < E; ++i) p[i] = m[i];
+          M::F_apply(fv, p);
         }
         if (a.flags & FLAG_Q_DIAG) {
           // diagonal process noise: only P[lane][lane] changes
