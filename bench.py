@@ -293,9 +293,118 @@ def run_gpu(args):
       line["final_gather_ms"] = gather_ms
     if not args.no_cpu_baseline and world == 1:
       line["cpu_baseline"] = cpu_reference(fname, args.workload, budget_s=args.cpu_budget)
+    if args.extras and world == 1:
+      del eng, streamer, dpools
+      torch.cuda.empty_cache()
+      try:
+        line["extras"] = run_extras(dev, peak)
+      except Exception as ex:  # pylint: disable=broad-except
+        line["extras"] = {"error": repr(ex)[:300]}
     print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ secondary kernels (extras) ---
+def _time_ms(fn, iters, torch, dev):
+  fn(); torch.cuda.synchronize(dev)
+  t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t0.record()
+  for _ in range(iters):
+    fn()
+  t1.record(); torch.cuda.synchronize(dev)
+  return t0.elapsed_time(t1) / iters
+
+
+def run_extras(dev, peak):
+  """Short measurements of the other kernels of the path so every one has a number beside its roofline:
+  kinematic (thread-per-filter), RTS backward pass, forward pass with history, MSCKF (CTA-per-filter)."""
+  import torch
+  from rednose_b200.batched import BatchedEKF
+  from rednose_b200.filters import ensure_generated
+  out = {}
+  # kinematic: 1M (fits L2) and 16M (HBM)
+  from rednose_b200.filters.kinematic import KinematicKalman
+  d = ensure_generated(KinematicKalman)
+  for label, B in (("kinematic_1m", 1 << 20), ("kinematic_16m", 1 << 24)):
+    x0, P0, Q, pools, _, _ = make_problem("kinematic", B, 7, d)
+    e = BatchedEKF(d, "kinematic", Q, x0, P0, device=dev)
+    zp, R = torch.as_tensor(pools[1][0][0]).to(dev), torch.as_tensor(pools[1][1]).to(dev)
+    dt = torch.full((B,), 0.01, dtype=torch.float64, device=dev)
+    zw = torch.empty(B, 1, 1, dtype=torch.float64, device=dev)
+    def step():
+      zw[:, 0, :].copy_(zp)
+      e.step(1, dt, zw, R)
+    ms = _time_ms(step, 50, torch, dev)
+    out[label] = {"ms_per_step": ms, "steps_per_s": B / (ms * 1e-3), "GBps_algorithmic": bytes_per_step(2, 2, 1) * B / (ms * 1e-3) / 1e9,
+                  "frac_of_peak": bytes_per_step(2, 2, 1) * B / (ms * 1e-3) / 1e9 / peak, "note": "includes the 8 B/filter observation refresh copy"}
+    del e, zp, R, dt, zw
+  # live: forward with history + RTS backward (tile of filters sized so the history fits comfortably)
+  from rednose_b200.filters.live import LiveKalman
+  d = ensure_generated(LiveKalman)
+  B, T = 1 << 16, 16
+  x0, P0, Q, pools, _, quat = make_problem("live", B, 11, d)
+  e = BatchedEKF(d, "live", Q, x0, P0, device=dev, quaternion_idxs=quat)
+  dpool = {k: (torch.as_tensor(z[0]).to(dev), torch.as_tensor(R[0]).to(dev)) for k, (z, R) in pools.items()}
+  hist = e.new_history(T)
+  sched = kind_schedule("live", T)
+  torch.cuda.synchronize(dev)
+  t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+  t0.record()
+  for k in range(T):
+    zk, Rk = dpool[sched[k]]
+    e.step_recorded(hist, sched[k], 0.01 * (k + 1), zk.clone(), Rk)
+  t1.record(); torch.cuda.synchronize(dev)
+  _fwd_ms = t0.elapsed_time(t1) / T
+  xs, Ps = e.rts_smooth(hist, norm_quats=True)   # warm-up (allocations)
+  torch.cuda.synchronize(dev)
+  t1.record()
+  xs, Ps = e.rts_smooth(hist, norm_quats=True)
+  t2.record(); torch.cuda.synchronize(dev)
+  bwd_ms = t1.elapsed_time(t2) / (T - 1)
+  torch.cuda.synchronize(dev)
+  fwd_ms = _fwd_ms
+  out["live_forward_with_history"] = {"filters": B, "T": T, "ms_per_step": fwd_ms, "steps_per_s": B / (fwd_ms * 1e-3),
+                                      "GBps_algorithmic": (8240 + 8120) * B / (fwd_ms * 1e-3) / 1e9, "frac_of_peak": (8240 + 8120) * B / (fwd_ms * 1e-3) / 1e9 / peak}
+  out["live_rts_backward"] = {"filters": B, "T": T, "ms_per_step": bwd_ms, "steps_per_s": B / (bwd_ms * 1e-3),
+                              "GBps_algorithmic": 12176 * B / (bwd_ms * 1e-3) / 1e9, "frac_of_peak": 12176 * B / (bwd_ms * 1e-3) / 1e9 / peak,
+                              "finite": bool(torch.isfinite(xs).all() and torch.isfinite(Ps).all())}
+  del e, hist, xs, Ps
+  # MSCKF 10k: fused predict + feature-track update (null-space projection + gate), CTA-per-filter
+  try:
+    from rednose_b200.ekf_sym import EKF_sym
+    from rednose_b200.filters.msckf import DIM, EDIM, MsckfKalman
+    d = ensure_generated(MsckfKalman)
+    B = 10_000
+    rng = np.random.default_rng(5)
+    xt = MsckfKalman.initial_x.copy()
+    q = np.array([0.7, 0.1, -0.5, 0.5]); q /= np.linalg.norm(q)
+    from rednose_b200.geometry import quat2rot
+    Rm = quat2rot(q)
+    xt[3:7] = q
+    for c in range(10):
+      o = 23 + 7 * c
+      xt[o:o + 3] = xt[0:3] - Rm[:, 0] * 0.5 * (10 - c)
+      xt[o + 3:o + 7] = q
+    point = xt[0:3] + Rm @ np.array([30.0, 2.0, -1.0])
+    kf = EKF_sym(d, "msckf", MsckfKalman.Q, xt, np.diag(MsckfKalman.initial_P_diag), 23, 22, N=10, dim_augment=7, dim_augment_err=6)
+    hz = np.zeros(20)
+    kf.hs[17](xt, point, hz)
+    x0 = np.tile(xt, (B, 1)); x0[:, 0:3] += rng.normal(0, 0.5, (B, 3))
+    pd = np.concatenate([[25.0] * 3 + [0.05**2] * 3 + [1.0] * 3 + [0.1**2] * 3 + [0.01**2] * 3 + [0.01**2] + [0.5**2] * 3 + [0.01**2] * 3] + [[1.0] * 3 + [0.02**2] * 3] * 10)
+    e = BatchedEKF(d, "msckf", MsckfKalman.Q, x0, np.diag(pd), batch=B, device=dev, quaternion_idxs=[3] + [26 + 7 * c for c in range(10)])
+    zp = torch.as_tensor(hz[None, :] + rng.normal(0, 1e-3, (B, 20))).to(dev)
+    Rk = torch.as_tensor(np.eye(20) * 1e-6).to(dev)
+    ea = torch.as_tensor(np.tile(point, (B, 1))).to(dev)
+    def mstep():
+      e.step(17, 0.01, zp.clone(), Rk, ea=ea)
+    ms = _time_ms(mstep, 10, torch, dev)
+    bs = 8 * (2 * EDIM * EDIM + 2 * DIM + 20 + 400 + 17 + 3 + 1)
+    out["msckf_10k_feature_step"] = {"filters": B, "ms_per_step": ms, "steps_per_s": B / (ms * 1e-3), "GBps_algorithmic": bs * B / (ms * 1e-3) / 1e9,
+                                     "frac_of_peak": bs * B / (ms * 1e-3) / 1e9 / peak, "finite": bool(torch.isfinite(e.x).all())}
+  except Exception as ex:  # pylint: disable=broad-except
+    out["msckf_10k_feature_step"] = {"error": repr(ex)[:200]}
+  return out
 
 
 # ------------------------------------------------------------------- reference arm / CPU baseline ---
@@ -396,6 +505,7 @@ def main():
   ap.add_argument("--e2e-steps", type=int, default=20)
   ap.add_argument("--cpu-budget", type=float, default=15.0)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--extras", action="store_true", help="also time the kinematic / RTS / history / MSCKF kernels (adds ~1 min)")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3)
   if args.impl == "reference":

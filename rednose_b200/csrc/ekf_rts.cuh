@@ -48,13 +48,18 @@ struct RtsArgs {
 };
 
 constexpr int RTS_WARPS = 2;
+#ifndef RNB_RTS_MIN_CTAS
+#define RNB_RTS_MIN_CTAS 6
+#endif
+constexpr int RTS_MIN_CTAS = RNB_RTS_MIN_CTAS;
 
 template <class M>
 struct RtsScratch {
   static constexpr int N = M::MEDIM;
   static constexpr int LD = (N + 3) & ~1;             // even leading dimension (128-bit rows), not a multiple of 32 banks
-  alignas(16) double LT[N * LD];                      // LT[k][i] = L[i][k]
+  alignas(16) double LT[N * LD];                      // LT[k][i] = unscaled column k of the trailing matrix = D[k] L[i][k] (i >= k)
   alignas(16) double DP[N * LD];                      // dP = P_{k+1|N} - P_{k+1|k}; later X (row-major)
+  alignas(16) double YS[N * 32];                      // y = dP X, column per lane
   alignas(16) double xf[(M::DIM + 1) & ~1];           // x_{k|k}
   alignas(16) double xp[(M::DIM + 1) & ~1];           // x_{k+1|k}
   alignas(16) double xn[(M::DIM + 1) & ~1];           // x_{k+1|N} -> x_{k|N}
@@ -64,7 +69,7 @@ struct RtsScratch {
 };
 
 template <class M>
-__global__ void __launch_bounds__(RTS_WARPS * 32) ekf_rts_warp(const RtsArgs<M::NG> a) {
+__global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp(const RtsArgs<M::NG> a) {
   constexpr int D = M::DIM, E = M::EDIM, N = M::MEDIM, D1 = M::DMAIN;
   using SC = RtsScratch<M>;
   constexpr int LD = SC::LD;
@@ -78,6 +83,16 @@ __global__ void __launch_bounds__(RTS_WARPS * 32) ekf_rts_warp(const RtsArgs<M::
   const bool actE = lane < E;       // owns a column of the full covariance
   const int col = actE ? lane : 0;
   const long long BP = a.B * (long long)(E * E), BX = a.B * (long long)D;
+
+  auto normalize_xn = [&]() {
+    for (int q = 0; q < a.n_quat; ++q) {
+      double* qp = s.xn + a.quat_idx[q];
+      const double nrm = sqrt(qp[0] * qp[0] + qp[1] * qp[1] + qp[2] * qp[2] + qp[3] * qp[3]);
+      __syncwarp();
+      if (lane < 4) qp[lane] = qp[lane] / nrm;
+      __syncwarp();
+    }
+  };
 
   // ---- start: x_{T-1|N} = x_{T-1|T-2} (predicted), P likewise (ekf_sym.py:658-659) ----
   double pn[N];  // column `lane` of the carried smoothed covariance (main block)
@@ -93,15 +108,7 @@ __global__ void __launch_bounds__(RTS_WARPS * 32) ekf_rts_warp(const RtsArgs<M::
     }
     for (int i = lane; i < D; i += 32) s.xn[i] = a.hx_pred[k * BX + b * D + i];
     __syncwarp();
-    if (a.norm_quats && a.T >= 2) {
-      for (int q = 0; q < a.n_quat; ++q) {
-        double* qp = s.xn + a.quat_idx[q];
-        const double nrm = sqrt(qp[0] * qp[0] + qp[1] * qp[1] + qp[2] * qp[2] + qp[3] * qp[3]);
-        __syncwarp();
-        if (lane < 4) qp[lane] = qp[lane] / nrm;
-        __syncwarp();
-      }
-    }
+    if (a.norm_quats && a.T >= 2) normalize_xn();
     for (int i = lane; i < D; i += 32) a.xs[k * BX + b * D + i] = s.xn[i];
   }
 
@@ -109,9 +116,9 @@ __global__ void __launch_bounds__(RTS_WARPS * 32) ekf_rts_warp(const RtsArgs<M::
   for (long long k = a.T - 2; k >= 0; --k) {
     const double* Pf_g = a.hP_filt + k * BP + b * (long long)(E * E) + col;
     const double* Pp_g = a.hP_pred + (k + 1) * BP + b * (long long)(E * E) + col;
-    double A[N], g[N];
+    double g[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) { A[i] = Pp_g[i * E]; g[i] = Pf_g[i * E]; }
+    for (int i = 0; i < N; ++i) g[i] = Pf_g[i * E];
     for (int i = lane; i < D; i += 32) {
       s.xf[i] = a.hx_filt[k * BX + b * D + i];
       s.xp[i] = a.hx_pred[(k + 1) * BX + b * D + i];
@@ -119,48 +126,63 @@ __global__ void __launch_bounds__(RTS_WARPS * 32) ekf_rts_warp(const RtsArgs<M::
     const double dt = a.t_per_filter ? (a.t[(k + 1) * a.B + b] - a.t[k * a.B + b]) : (a.t[k + 1] - a.t[k]);
     __syncwarp();
 
-    // dP column (before the factorisation destroys A)
-    if (act) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) s.DP[i * LD + lane] = pn[i] - A[i];
-    }
-
     // G[:,lane] = F P_{k|k}[:,lane]   (F evaluated at the filtered state)
     {
       double fv[M::NF > 0 ? M::NF : 1];
       M::F_vals(s.xf, dt, a.gv, fv);
       M::F_apply(fv, g);
     }
+    asm volatile("" ::: "memory");  // scheduling fence: keep the next loads below the leaf code (register pressure)
 
-    // ---- P_{k+1|k} = L D L^T : right-looking, one column broadcast per step ----
+    // A = column of P_{k+1|k};  dP column = P_{k+1|N} - P_{k+1|k} (pn is dead afterwards)
+    double A[N];
 #pragma unroll
+    for (int i = 0; i < N; ++i) A[i] = Pp_g[i * E];
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) s.DP[i * LD + lane] = pn[i] - A[i];
+    }
+
+    // ---- P_{k+1|k} = L D L^T : right-looking, one (unscaled) column broadcast per step.  The outer loop is
+    //      NOT unrolled (code size); register arrays are only indexed statically: lane kk publishes its
+    //      column c = A_kk[:], every lane then needs c[lane] (= its own A[kk] by symmetry) and c[i]. ----
+#pragma unroll 1
     for (int kk = 0; kk < N; ++kk) {
       if (lane == kk) {
-        const double di = 1.0 / A[kk];
-        s.dinv[kk] = di;
 #pragma unroll
-        for (int i = kk + 1; i < N; ++i) s.LT[kk * LD + i] = A[i] * di;
+        for (int i = 0; i < N; ++i) s.LT[kk * LD + i] = A[i];
       }
       __syncwarp();
-      // A[i][j] -= L[i][kk] * (D[kk] L[j][kk]);  D[kk] L[j][kk] = A[kk][j] = this lane's A[kk] (symmetry)
-      const double akk = A[kk];
+      const double di = 1.0 / s.LT[kk * LD + kk];
+      if (lane == 0) s.dinv[kk] = di;
+      const double cj = s.LT[kk * LD + (act ? lane : 0)] * di;   // D[kk] L[lane][kk] / D[kk] ... = L[lane][kk]
 #pragma unroll
-      for (int i = kk + 1; i < N; ++i) A[i] = fma(-s.LT[kk * LD + i], akk, A[i]);
+      for (int i = 0; i < N; i += 2) {
+        const double2 c2 = *reinterpret_cast<const double2*>(&s.LT[kk * LD + i]);
+        if (i > kk) A[i] = fma(-c2.x, cj, A[i]);
+        if (i + 1 > kk && i + 1 < N) A[i + 1] = fma(-c2.y, cj, A[i + 1]);
+      }
     }
-    // ---- X[:,lane] = (L D L^T)^-1 G[:,lane] ----
+    __syncwarp();
+    // ---- X[:,lane] = (L D L^T)^-1 G[:,lane];  L[i][kk] = LT[kk][i] * dinv[kk] ----
 #pragma unroll
     for (int kk = 0; kk < N; ++kk) {
+      const double gk = g[kk] * s.dinv[kk];
 #pragma unroll
-      for (int i = kk + 1; i < N; ++i) g[i] = fma(-s.LT[kk * LD + i], g[kk], g[i]);
+      for (int i = kk + 1; i < N; ++i) g[i] = fma(-s.LT[kk * LD + i], gk, g[i]);
+      asm volatile("" ::: "memory");  // keep ptxas from hoisting every row of L into registers at once
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] *= s.dinv[i];
 #pragma unroll
-    for (int kk = N - 2; kk >= 0; --kk) {
-      double acc = g[kk];
+    const volatile double* LTv = s.LT;  // re-read L: without this ptxas keeps all of L from the forward sweep (spills)
 #pragma unroll
-      for (int i = kk + 1; i < N; ++i) acc = fma(-s.LT[kk * LD + i], g[i], acc);
-      g[kk] = acc;
+    for (int kk = N - 2; kk >= 0; --kk) {
+      double acc = 0.0;
+#pragma unroll
+      for (int i = kk + 1; i < N; ++i) acc = fma(LTv[kk * LD + i], g[i], acc);
+      g[kk] = fma(-acc, s.dinv[kk], g[kk]);
+      asm volatile("" ::: "memory");
     }
     // g = X[:,lane] = row `lane` of C
 
@@ -177,21 +199,12 @@ __global__ void __launch_bounds__(RTS_WARPS * 32) ekf_rts_warp(const RtsArgs<M::
     __syncwarp();
     for (int i = lane; i < D; i += 32) s.xn[i] = (i < D1) ? s.xt[i] : s.xf[i];
     __syncwarp();
-    if (a.norm_quats && k >= 1) {
-      for (int q = 0; q < a.n_quat; ++q) {
-        double* qp = s.xn + a.quat_idx[q];
-        const double nrm = sqrt(qp[0] * qp[0] + qp[1] * qp[1] + qp[2] * qp[2] + qp[3] * qp[3]);
-        __syncwarp();
-        if (lane < 4) qp[lane] = qp[lane] / nrm;
-        __syncwarp();
-      }
-    }
+    if (a.norm_quats && k >= 1) normalize_xn();
     for (int i = lane; i < D; i += 32) a.xs[k * BX + b * D + i] = s.xn[i];
 
     // ---- covariance: P_{k|N} = P_{k|k} + X^T (dP X) ----
-    double y[N];  // y = dP X[:,lane]
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {   // y[i] = dP[i,:] . X[:,lane]
       double acc = 0.0;
 #pragma unroll
       for (int c = 0; c < N; c += 2) {
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(RTS_WARPS * 32) ekf_rts_warp(const RtsArgs<M::
         acc = fma(d2.x, g[c], acc);
         if (c + 1 < N) acc = fma(d2.y, g[c + 1], acc);
       }
-      y[i] = acc;
+      s.YS[i * 32 + lane] = acc;
     }
     __syncwarp();
     if (act) {  // X row-major into the dP buffer: XS[r][lane] = X[r][lane]
@@ -207,32 +220,26 @@ __global__ void __launch_bounds__(RTS_WARPS * 32) ekf_rts_warp(const RtsArgs<M::
       for (int i = 0; i < N; ++i) s.DP[i * LD + lane] = g[i];
     }
     __syncwarp();
-    // reload P_{k|k} column (cheaper than keeping it live across the factorisation)
-    double pf[E];
+    // out = P_{k|k}[:, lane] + sum_r X[r][:] y[r]
 #pragma unroll
-    for (int i = 0; i < E; ++i) pf[i] = Pf_g[i * E];
-#pragma unroll
+    for (int i = 0; i < N; ++i) pn[i] = Pf_g[i * E];
+#pragma unroll 1
     for (int r = 0; r < N; ++r) {
-      // out[i] += X[r][i] * y[r]
+      const double yr = s.YS[r * 32 + lane];
 #pragma unroll
       for (int i = 0; i < N; i += 2) {
         const double2 x2 = *reinterpret_cast<const double2*>(&s.DP[r * LD + i]);
-        pf[i] = fma(x2.x, y[r], pf[i]);
-        if (i + 1 < N) pf[i + 1] = fma(x2.y, y[r], pf[i + 1]);
+        pn[i] = fma(x2.x, yr, pn[i]);
+        if (i + 1 < N) pn[i + 1] = fma(x2.y, yr, pn[i + 1]);
       }
     }
-    // lanes outside the main block keep P_{k|k} (only the main block is smoothed, ekf_sym.py:686)
+    // lanes / rows outside the main block keep P_{k|k} (only the main block is smoothed, ekf_sym.py:686)
     if (actE) {
       const double* Pfull = a.hP_filt + k * BP + b * (long long)(E * E) + col;
       double* Po = a.Ps + k * BP + b * (long long)(E * E) + col;
 #pragma unroll
-      for (int i = 0; i < E; ++i) {
-        const double v = (act && i < N) ? pf[i] : Pfull[i * E];
-        Po[i * E] = v;
-      }
+      for (int i = 0; i < E; ++i) Po[i * E] = (act && i < N) ? pn[i < N ? i : 0] : Pfull[i * E];
     }
-#pragma unroll
-    for (int i = 0; i < N; ++i) pn[i] = pf[i];
     __syncwarp();
   }
 }
