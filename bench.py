@@ -267,6 +267,14 @@ def run_gpu(args):
     dom_ms = float(np.mean(per_kind[dom]))
     algo = bytes_per_step(dim, edim, zdim[dom]) * B
     achieved = algo / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # measured DRAM bytes per launch of this kernel from the committed ncu capture (same batch size only)
+      with open(os.path.join(REPO, "profiles", "traffic.json"), encoding="utf-8") as f:
+        tj = json.load(f)
+      if B == 1 << 20:
+        traffic = tj.get(f"ekf_step<{fname}, kind {dom}>")
+    except Exception:  # pylint: disable=broad-except
+      pass
     total_steps = B * args.steps * world
     line = {
       "metric": "fused EKF predict+update steps/s (batched, float64)",
@@ -283,8 +291,8 @@ def run_gpu(args):
       "gpu_launches": launches,
       "per_kind_ms": {str(k): float(np.mean(v)) for k, v in per_kind.items()},
       "roofline": {"bound": "hbm", "kernel": f"ekf_step<{fname}, kind {dom}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                   "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_step": bytes_per_step(dim, edim, zdim[dom]),
-                   "traffic": None},
+                   "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_step": bytes_per_step(dim, edim, zdim[dom]), "algorithmic_bytes_per_launch": algo,
+                   "traffic": traffic},
       "e2e": {"value": B * e2e_steps * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
               "steps": e2e_steps, "what": "HostStreamer.submit(t, kind, z_pinned_host, R_kind): H2D of z, fused step, D2H of x and y into pinned host memory EVERY step (3 streams overlap consecutive steps); P stays resident"},
       "clocks": clocks.summary(),

@@ -32,7 +32,7 @@ namespace rnb {
 
 // tuning knobs (overridable at build time: -DRNB_GROUP=..., -DRNB_WARPS=...)
 #ifndef RNB_GROUP
-#define RNB_GROUP 12  // filters per warp group (leaf phase uses RNB_GROUP of the 32 lanes)
+#define RNB_GROUP 14  // filters per warp group (leaf phase uses RNB_GROUP of the 32 lanes)
 #endif
 #ifndef RNB_WARPS
 #define RNB_WARPS 1    // warps per CTA (warps never synchronise with each other)
@@ -121,9 +121,11 @@ struct WarpScratch {
   alignas(128) double tile[(NST > 0 ? NST : 1) * (use_tma<M>() ? M::EDIM * M::EDIM : 2)];  // covariance tiles (TMA ring)
   alignas(8) uint64_t full[NST > 0 ? NST : 1];                                              // "tile landed" mbarriers
   alignas(16) double rows[G * L::STRIDE];
-  static constexpr int EXS = 33;                                 // exchange row stride (odd: conflict-free column writes)
-  alignas(16) double ex[(M::NFROWS > 0 ? M::NFROWS : 1) * EXS];  // row exchange for F P F^T
-  alignas(16) double hp[K::ZDIM * 32];                          // (H P)[c][k]
+  static constexpr int EXS = M::EDIM | 1;                        // exchange row stride (odd: conflict-free column writes)
+  static constexpr int EXN = (M::NFROWS > 0 ? M::NFROWS : 1) * EXS + 32;
+  static constexpr int HPN = K::ZDIM * 32;
+  // one buffer, two lives: row exchange for F P F^T during the predict, then (H P)[c][k] during the update
+  alignas(16) double exhp[EXN > HPN ? EXN : HPN];
 };
 
 // normalise quaternions of a state held in shared memory (private to the calling lane)
@@ -326,13 +328,13 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
 #pragma unroll
             for (int i = 0; i < E; ++i) m[i] = p[i];
             M::F_apply(fv, m);                      // only the non-identity rows of m are computed / used
-            M::frows_store(m, s.ex + lane, EXS);
+            if (act) M::frows_store(m, s.exhp + lane, EXS);   // stride < 32: idle lanes must not spill into the next row
           }
           __syncwarp();
           const bool in_rf = (M::FROW_MASK >> lane) & 1u;
           const int slot_rf = __popc(M::FROW_MASK & ((1u << lane) - 1u));
           if (in_rf) {  // this lane's row of F P replaces its column of P
-            const double* xr = s.ex + slot_rf * EXS;
+            const double* xr = s.exhp + slot_rf * EXS;
 #pragma unroll
             for (int i = 0; i < E; ++i) p[i] = xr[i];
           }
@@ -366,14 +368,14 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
           vec_load(row + L::OFF_HV, hv);
           K::Herr_apply(hv, p, hp);  // (H P)[:,lane]
 #pragma unroll
-          for (int c = 0; c < Z; ++c) s.hp[c * 32 + lane] = act ? hp[c] : 0.0;
+          for (int c = 0; c < Z; ++c) s.exhp[c * 32 + lane] = act ? hp[c] : 0.0;
           __syncwarp();
           // S = H_err (H P)^T + R, warp-uniform
 #pragma unroll
           for (int i = 0; i < Z; ++i)
 #pragma unroll
             for (int j = 0; j < Z; ++j) S[i][j] = 0.0;
-          K::S_accum(hv, [&](int c, int k) { return s.hp[c * 32 + k]; }, S);
+          K::S_accum(hv, [&](int c, int k) { return s.exhp[c * 32 + k]; }, S);
         }
         double y[L::Zp], R[L::ZZp];
         vec_load(row + L::OFF_Y, y);
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
           double a0 = p[i], a1 = (i + 1 < E) ? p[i + 1] : 0.0;
 #pragma unroll
           for (int c = 0; c < Z; ++c) {
-            const double2 h2 = *reinterpret_cast<const double2*>(&s.hp[c * 32 + i]);
+            const double2 h2 = *reinterpret_cast<const double2*>(&s.exhp[c * 32 + i]);
             a0 = fma(-h2.x, hp[c], a0);
             a1 = fma(-h2.y, hp[c], a1);
           }
