@@ -59,3 +59,13 @@ def test_include_header_compiles_as_c(tmp_path):
   src = tmp_path / "t.c"
   src.write_text('#include "rednose_b200.h"\nint main(void){ rednose_ekf_desc d; (void)d; return 0; }\n')
   subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", f"-I{INCLUDE_DIR}", "-c", str(src), "-o", str(tmp_path / "t.o")], check=True)
+
+
+def test_generator_features_symbols(gen_dir):
+  """global_vars -> <name>_set_<var>, extra_routines -> <name>_<routine> (ekf_sym.py:94-95,166-171)."""
+  from rednose_b200.filters import ensure_generated
+  from rednose_b200.filters.pendulum import PendulumKalman
+  d = ensure_generated(PendulumKalman)
+  lib = ctypes.CDLL(os.path.join(d, "libpendulum.so"))
+  for sym in ("pendulum_set_grav", "pendulum_set_damp", "pendulum_energy", "pendulum_update_2", "pendulum_batch_step_2"):
+    assert hasattr(lib, sym)
