@@ -31,7 +31,8 @@ struct CtaWs {  // per-filter workspace record (doubles)
   static constexpr int OFF_Y = OFF_DT + 1;
   static constexpr int OFF_HV = OFF_Y + K::ZDIM;
   static constexpr int OFF_HE = OFF_HV + (K::NH > 0 ? K::NH : 1);
-  static constexpr int SIZE = OFF_HE + (K::HAS_HE ? K::ZDIM * K::EADIM : 0);
+  // feature kinds: Householder vectors V [NR][Z] of He (NR = EADIM) followed by the NR scalars beta
+  static constexpr int SIZE = OFF_HE + (K::HAS_HE ? K::ZDIM * K::EADIM + K::EADIM : 0);
 };
 
 // ------------------------------------------------------------------ leaf kernel ---
@@ -84,7 +85,42 @@ __global__ void __launch_bounds__(64) ekf_leaf_thread(const StepArgs<M::NG> a, i
     K::obs_leaf(x, ea, a.gv, hx, *reinterpret_cast<double(*)[K::NH > 0 ? K::NH : 1]>(ws + W::OFF_HV));
 #pragma unroll
     for (int i = 0; i < Z; ++i) ws[W::OFF_Y + i] = a.z[bo * Z + i] - hx[i];
-    if constexpr (K::HAS_HE) K::He_dense(x, ea, a.gv, ws + W::OFF_HE);
+    if constexpr (K::HAS_HE) {
+      // Householder QR of He (Z x EA) done here, one filter per thread: Q = H_1 .. H_EA, the left null space of
+      // He is spanned by the last Z - EA columns of Q (ekf_c.c:66-76 takes fullPivLu().kernel() of He^T instead)
+      constexpr int EA = K::EADIM;
+      double He[Z * EA];
+      K::He_dense(x, ea, a.gv, He);
+#pragma unroll
+      for (int r = 0; r < EA; ++r) {
+        double nrm = 0.0;
+#pragma unroll
+        for (int i = r; i < Z; ++i) nrm = fma(He[i * EA + r], He[i * EA + r], nrm);
+        nrm = sqrt(nrm);
+        const double a0 = He[r * EA + r];
+        const double alpha = (a0 >= 0.0) ? -nrm : nrm;
+        double v[Z];
+#pragma unroll
+        for (int i = 0; i < Z; ++i) v[i] = (i < r) ? 0.0 : He[i * EA + r];
+        v[r] = a0 - alpha;
+        double vn = 0.0;
+#pragma unroll
+        for (int i = r; i < Z; ++i) vn = fma(v[i], v[i], vn);
+        const double beta = (vn > 0.0) ? 2.0 / vn : 0.0;
+#pragma unroll
+        for (int c = r + 1; c < EA; ++c) {
+          double w = 0.0;
+#pragma unroll
+          for (int i = r; i < Z; ++i) w = fma(v[i], He[i * EA + c], w);
+          w *= beta;
+#pragma unroll
+          for (int i = r; i < Z; ++i) He[i * EA + c] = fma(-w, v[i], He[i * EA + c]);
+        }
+#pragma unroll
+        for (int i = 0; i < Z; ++i) ws[W::OFF_HE + r * Z + i] = v[i];
+        ws[W::OFF_HE + EA * Z + r] = beta;
+      }
+    }
   }
 }
 
@@ -103,7 +139,6 @@ struct CtaSmem {
   double dinv[Z];
   double V[(K::HAS_HE ? K::EADIM : 1) * Z];        // Householder vectors of He
   double beta[K::HAS_HE ? K::EADIM : 1];
-  double He[K::HAS_HE ? Z * K::EADIM : 1];
   double y[Z];
   double hv[K::NH > 0 ? K::NH : 1];
   double fv[M::NF > 0 ? M::NF : 1];
@@ -133,19 +168,26 @@ __device__ __forceinline__ void apply_reflectors(const double* V, const double* 
   }
 }
 
+template <class M>
+constexpr int cta_tpg() { return ((M::EDIM + 31) / 32) * 32; }   // threads per group: one per column
+constexpr int CTA_GROUPS = 2;                                      // groups split the rows of the rank-m covariance update
+
 template <class M, class K, bool PRED, bool UPD>
-__global__ void __launch_bounds__(((M::EDIM + 31) / 32) * 32) ekf_step_cta(const StepArgs<M::NG> a, int o, const double* __restrict__ ws_all) {
+__global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS) ekf_step_cta(const StepArgs<M::NG> a, int o, const double* __restrict__ ws_all) {
   constexpr int D = M::DIM, E = M::EDIM, ME = M::MEDIM, Z = K::ZDIM, Y = K::YDIM, NR = Z - Y;
   using SM = CtaSmem<M, K>;
   using W = CtaWs<M, K>;
   constexpr int LD = SM::LD, HL = SM::HL, SL = SM::SL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM& s = *reinterpret_cast<SM*>(smem_raw);
+  constexpr int TPG = cta_tpg<M>();
   const int tid = threadIdx.x, nth = blockDim.x;
+  const int grp = tid / TPG, col = tid - grp * TPG;   // group 0 does the per-column work, all groups share the big row loops
   const long long b = blockIdx.x;
   const double* ws = ws_all + b * W::SIZE;
   double* Pg = a.P + b * (long long)(E * E);
-  const bool own = tid < E;
+  const bool own = col < E;            // this thread is attached to column `col`
+  const bool own0 = own && grp == 0;   // ... and is the one that writes per-column results
 
   // ---- stage: covariance tile (coalesced, re-pitched), leaf values ----
   for (int idx = tid; idx < E * E; idx += nth) {
@@ -160,7 +202,10 @@ __global__ void __launch_bounds__(((M::EDIM + 31) / 32) * 32) ekf_step_cta(const
   if constexpr (UPD) {
     for (int i = tid; i < (K::NH > 0 ? K::NH : 1); i += nth) s.hv[i] = ws[W::OFF_HV + i];
     for (int i = tid; i < Z; i += nth) s.y[i] = ws[W::OFF_Y + i];
-    if constexpr (K::HAS_HE) for (int i = tid; i < Z * K::EADIM; i += nth) s.He[i] = ws[W::OFF_HE + i];
+    if constexpr (K::HAS_HE) {
+      for (int i = tid; i < Z * K::EADIM; i += nth) s.V[i] = ws[W::OFF_HE + i];
+      for (int i = tid; i < K::EADIM; i += nth) s.beta[i] = ws[W::OFF_HE + Z * K::EADIM + i];
+    }
     const double* Rg = a.R + ((a.flags & FLAG_SHARED_R) ? 0 : (b * a.n_obs + o) * (long long)(Z * Z));
     for (int idx = tid; idx < Z * Z; idx += nth) s.Rm[(idx / Z) * SL + idx % Z] = Rg[idx];
     if (tid == 0) s.gated = 0;
@@ -169,28 +214,31 @@ __global__ void __launch_bounds__(((M::EDIM + 31) / 32) * 32) ekf_step_cta(const
 
   // =============================== predict: P <- F P F^T + dt Q (main block) ===============================
   if constexpr (PRED) {
-    if (own) {  // column tid: (F P)[:, tid]
+    if (own0) {  // column col: (F P)[:, col]
       double v[ME];
 #pragma unroll
-      for (int i = 0; i < ME; ++i) v[i] = s.P[i * LD + tid];
+      for (int i = 0; i < ME; ++i) v[i] = s.P[i * LD + col];
       M::F_apply(s.fv, v);
-      M::frows_scatter(v, &s.P[tid], LD);  // only the rows of F that differ from the identity change
+      M::frows_scatter(v, &s.P[col], LD);  // only the rows of F that differ from the identity change
     }
     __syncthreads();
-    if (own) {  // row tid: ((F P) F^T)[tid, :]
+    if (own0) {  // row col: ((F P) F^T)[col, :]
       double v[ME];
 #pragma unroll
-      for (int k = 0; k < ME; ++k) v[k] = s.P[tid * LD + k];
+      for (int k = 0; k < ME; ++k) v[k] = s.P[col * LD + k];
       M::F_apply(s.fv, v);
-      M::frows_scatter(v, &s.P[tid * LD], 1);
+      M::frows_scatter(v, &s.P[col * LD], 1);
     }
     __syncthreads();
-    if (own) {
+    {
       const double dt = s.dt;
       if (a.flags & FLAG_Q_DIAG) {
-        s.P[tid * LD + tid] += dt * __ldg(a.Q + tid * E + tid);
+        if (own0) s.P[col * LD + col] += dt * __ldg(a.Q + col * E + col);
       } else {
-        for (int i = 0; i < E; ++i) s.P[i * LD + tid] = fma(dt, __ldg(a.Q + i * E + tid), s.P[i * LD + tid]);
+        for (int idx = tid; idx < E * E; idx += nth) {
+          const int i = idx / E, j = idx - i * E;
+          s.P[i * LD + j] = fma(dt, __ldg(a.Q + idx), s.P[i * LD + j]);
+        }
       }
     }
     __syncthreads();
@@ -201,39 +249,15 @@ __global__ void __launch_bounds__(((M::EDIM + 31) / 32) * 32) ekf_step_cta(const
   }
 
   if constexpr (UPD) {
-    // ---- Householder QR of He (Z x NR): Q = H_1 ... H_NR, left null space = last Y columns of Q ----
-    if constexpr (K::HAS_HE) {
-      if (tid == 0) {
-        constexpr int EA = K::EADIM;
-        for (int r = 0; r < NR; ++r) {
-          double nrm = 0.0;
-          for (int i = r; i < Z; ++i) nrm += s.He[i * EA + r] * s.He[i * EA + r];
-          nrm = sqrt(nrm);
-          const double a0 = s.He[r * EA + r];
-          const double alpha = (a0 >= 0.0) ? -nrm : nrm;
-          for (int i = 0; i < Z; ++i) s.V[r * Z + i] = (i < r) ? 0.0 : s.He[i * EA + r];
-          s.V[r * Z + r] = a0 - alpha;
-          double vn = 0.0;
-          for (int i = r; i < Z; ++i) vn += s.V[r * Z + i] * s.V[r * Z + i];
-          s.beta[r] = (vn > 0.0) ? 2.0 / vn : 0.0;
-          for (int c = r + 1; c < EA; ++c) {  // update the remaining columns of He
-            double w = 0.0;
-            for (int i = r; i < Z; ++i) w += s.V[r * Z + i] * s.He[i * EA + c];
-            w *= s.beta[r];
-            for (int i = r; i < Z; ++i) s.He[i * EA + c] -= w * s.V[r * Z + i];
-          }
-        }
-      }
-      __syncthreads();
-    }
-
-    // ---- HP_raw[:, tid] = H_err P[:, tid] (sparse), projected: hp <- (Q^T hp)[NR:] ----
+    // ---- HP_raw[:, col] = H_err P[:, col] (sparse); every group keeps its own copy in registers ----
     double hp[Z];
     if (own) {
-      SmemCol<Z> pc{&s.P[tid], LD};
+      SmemCol<Z> pc{&s.P[col], LD};
       K::Herr_apply(s.hv, pc, hp);
+      if (grp == 0) {
 #pragma unroll
-      for (int c = 0; c < Z; ++c) s.HP[tid * HL + c] = hp[c];  // unprojected, for S
+        for (int c = 0; c < Z; ++c) s.HP[col * HL + c] = hp[c];  // unprojected, for S
+      }
     }
     __syncthreads();
     // S_raw[:, t] = H_err (HP_raw[t, :])^T   (P symmetric)
@@ -246,27 +270,29 @@ __global__ void __launch_bounds__(((M::EDIM + 31) / 32) * 32) ekf_step_cta(const
     }
     __syncthreads();
     if constexpr (K::HAS_HE) {
-      // project S and R on both sides, y and HP on the left
-      if (tid < Z) {  // columns
-        double u[Z], r[Z];
+      // project S and R on both sides, y and HP on the left; S and R are handled by two different warps
+      const int w = tid >> 5, t = tid & 31;
+      if (w < 2 && t < Z) {  // columns
+        double* Mx = (w == 0) ? s.S : s.Rm;
+        double u[Z];
 #pragma unroll
-        for (int c = 0; c < Z; ++c) { u[c] = s.S[c * SL + tid]; r[c] = s.Rm[c * SL + tid]; }
+        for (int c = 0; c < Z; ++c) u[c] = Mx[c * SL + t];
         apply_reflectors<Z, NR>(s.V, s.beta, u);
-        apply_reflectors<Z, NR>(s.V, s.beta, r);
 #pragma unroll
-        for (int c = 0; c < Z; ++c) { s.S[c * SL + tid] = u[c]; s.Rm[c * SL + tid] = r[c]; }
+        for (int c = 0; c < Z; ++c) Mx[c * SL + t] = u[c];
       }
+      if (own) apply_reflectors<Z, NR>(s.V, s.beta, hp);
       __syncthreads();
-      if (tid < Z) {  // rows
-        double u[Z], r[Z];
+      if (w < 2 && t < Z) {  // rows
+        double* Mx = (w == 0) ? s.S : s.Rm;
+        double u[Z];
 #pragma unroll
-        for (int c = 0; c < Z; ++c) { u[c] = s.S[tid * SL + c]; r[c] = s.Rm[tid * SL + c]; }
+        for (int c = 0; c < Z; ++c) u[c] = Mx[t * SL + c];
         apply_reflectors<Z, NR>(s.V, s.beta, u);
-        apply_reflectors<Z, NR>(s.V, s.beta, r);
 #pragma unroll
-        for (int c = 0; c < Z; ++c) { s.S[tid * SL + c] = u[c]; s.Rm[tid * SL + c] = r[c]; }
+        for (int c = 0; c < Z; ++c) Mx[t * SL + c] = u[c];
       }
-      if (tid == Z) {  // one spare thread projects the innovation
+      if (w == 2 && t == 0) {  // the innovation
         double u[Z];
 #pragma unroll
         for (int c = 0; c < Z; ++c) u[c] = s.y[c];
@@ -274,15 +300,13 @@ __global__ void __launch_bounds__(((M::EDIM + 31) / 32) * 32) ekf_step_cta(const
 #pragma unroll
         for (int c = 0; c < Z; ++c) s.y[c] = u[c];
       }
-      if (own) {
-        apply_reflectors<Z, NR>(s.V, s.beta, hp);
-      }
       __syncthreads();
     }
     // from here on only the trailing Y x Y block / Y entries are used (offset NR)
-    if (own) {
+    if (own0) {
 #pragma unroll
-      for (int c = 0; c < Y; ++c) s.HP[tid * HL + c] = hp[NR + c];
+      for (int c = 0; c < Y; ++c) s.HP[col * HL + c] = hp[NR + c];
+      if (Y < HL) s.HP[col * HL + Y] = 0.0;
     }
 
     // ---- factor S = S_raw + R (warp 0, lane j = column j), gate, refactor if gated ----
@@ -293,36 +317,35 @@ __global__ void __launch_bounds__(((M::EDIM + 31) / 32) * 32) ekf_step_cta(const
         const double rs = (K::MAHA && pass == 1) ? 1.0e16 : 1.0;  // ekf_c.c:92
 #pragma unroll
         for (int i = 0; i < Y; ++i) A[i] = s.S[(NR + i) * SL + NR + j] + rs * s.Rm[(NR + i) * SL + NR + j];
-#pragma unroll
+#pragma unroll 1
         for (int kk = 0; kk < Y; ++kk) {
+          // lane kk publishes its (unscaled) column; every lane needs c[lane] (= its own A[kk], symmetry) and c[i]
           if (tid == kk) {
-            const double di = 1.0 / A[kk];
-            s.dinv[kk] = di;
 #pragma unroll
-            for (int i = kk + 1; i < Y; ++i) s.LT[kk * SL + i] = A[i] * di;
+            for (int i = 0; i < Y; ++i) s.LT[kk * SL + i] = A[i];
           }
           __syncwarp();
-          const double akk = A[kk];
+          const double di = 1.0 / s.LT[kk * SL + kk];
+          if (tid == 0) s.dinv[kk] = di;
+          const double cj = s.LT[kk * SL + j] * di;
 #pragma unroll
-          for (int i = kk + 1; i < Y; ++i) A[i] = fma(-s.LT[kk * SL + i], akk, A[i]);
+          for (int i = 0; i < Y; ++i)
+            if (i > kk) A[i] = fma(-s.LT[kk * SL + i], cj, A[i]);
         }
+        __syncwarp();
         if (K::MAHA && pass == 0 && tid == 0) {
           double u[Y];
 #pragma unroll
           for (int i = 0; i < Y; ++i) u[i] = s.y[NR + i];
 #pragma unroll
-          for (int kk = 0; kk < Y; ++kk)
+          for (int kk = 0; kk < Y; ++kk) {
+            const double uk = u[kk] * s.dinv[kk];
 #pragma unroll
-            for (int i = kk + 1; i < Y; ++i) u[i] = fma(-s.LT[kk * SL + i], u[kk], u[i]);
+            for (int i = kk + 1; i < Y; ++i) u[i] = fma(-s.LT[kk * SL + i], uk, u[i]);
+          }
+          double d = 0.0;   // y^T S^-1 y = sum_k u_k^2 / D_k  (u = L^-1 y)
 #pragma unroll
-          for (int i = 0; i < Y; ++i) u[i] *= s.dinv[i];
-#pragma unroll
-          for (int kk = Y - 2; kk >= 0; --kk)
-#pragma unroll
-            for (int i = kk + 1; i < Y; ++i) u[kk] = fma(-s.LT[kk * SL + i], u[i], u[kk]);
-          double d = 0.0;
-#pragma unroll
-          for (int i = 0; i < Y; ++i) d = fma(s.y[NR + i], u[i], d);
+          for (int i = 0; i < Y; ++i) d = fma(u[i] * s.dinv[i], u[i], d);
           s.gated = d > K::MAHA_THRESH;
         }
       }
@@ -330,33 +353,49 @@ __global__ void __launch_bounds__(((M::EDIM + 31) / 32) * 32) ekf_step_cta(const
       if (!(K::MAHA && pass == 0 && s.gated)) break;
     }
 
-    // ---- gain row: w = S^-1 HP[:, tid]; dx; covariance ----
+    // ---- gain row: w = S^-1 HP[:, col] (every group, in registers); dx; covariance ----
     double w[Y];
     if (own) {
 #pragma unroll
       for (int c = 0; c < Y; ++c) w[c] = hp[NR + c];
 #pragma unroll
-      for (int kk = 0; kk < Y; ++kk)
+      for (int kk = 0; kk < Y; ++kk) {
+        const double wk = w[kk] * s.dinv[kk];
 #pragma unroll
-        for (int i = kk + 1; i < Y; ++i) w[i] = fma(-s.LT[kk * SL + i], w[kk], w[i]);
+        for (int i = kk + 1; i < Y; ++i) w[i] = fma(-s.LT[kk * SL + i], wk, w[i]);
+      }
 #pragma unroll
       for (int i = 0; i < Y; ++i) w[i] *= s.dinv[i];
+      const volatile double* LTv = s.LT;
 #pragma unroll
-      for (int kk = Y - 2; kk >= 0; --kk)
+      for (int kk = Y - 2; kk >= 0; --kk) {
+        double acc = 0.0;
 #pragma unroll
-        for (int i = kk + 1; i < Y; ++i) w[kk] = fma(-s.LT[kk * SL + i], w[i], w[kk]);
-      double dxl = 0.0;
+        for (int i = kk + 1; i < Y; ++i) acc = fma(LTv[kk * SL + i], w[i], acc);
+        w[kk] = fma(-acc, s.dinv[kk], w[kk]);
+      }
+      if (grp == 0) {
+        double dxl = 0.0;
 #pragma unroll
-      for (int c = 0; c < Y; ++c) dxl = fma(w[c], s.y[NR + c], dxl);
-      s.dx[tid] = dxl;
+        for (int c = 0; c < Y; ++c) dxl = fma(w[c], s.y[NR + c], dxl);
+        s.dx[col] = dxl;
+      }
     }
     __syncthreads();  // HP (projected) complete in shared memory
     if (own) {
-      for (int i = 0; i < E; ++i) {
-        double acc = s.P[i * LD + tid];
+      // P[:, col] -= HP^T w; the groups split the rows
+      constexpr int RPG = (E + CTA_GROUPS - 1) / CTA_GROUPS;
+      const int i0 = grp * RPG, i1 = (i0 + RPG < E) ? i0 + RPG : E;
+#pragma unroll 2
+      for (int i = i0; i < i1; ++i) {
+        double acc = s.P[i * LD + col];
 #pragma unroll
-        for (int c = 0; c < Y; ++c) acc = fma(-s.HP[i * HL + c], w[c], acc);
-        s.P[i * LD + tid] = acc;
+        for (int c = 0; c < Y; c += 2) {
+          const double2 h2 = *reinterpret_cast<const double2*>(&s.HP[i * HL + c]);
+          acc = fma(-h2.x, w[c], acc);
+          if (c + 1 < Y) acc = fma(-h2.y, w[c + 1], acc);
+        }
+        s.P[i * LD + col] = acc;
       }
     }
     // state injection (every thread evaluates the small generated function; identical values)
@@ -412,7 +451,7 @@ inline void launch_step_cta(const StepArgs<M::NG>& a, cudaStream_t st) {
     check(cudaFuncSetAttribute(ekf_step_cta<M, K, false, UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute");
     configured = true;
   }
-  constexpr int threads = ((M::EDIM + 31) / 32) * 32;
+  constexpr int threads = cta_tpg<M>() * CTA_GROUPS;
   const int n_obs = UPD ? a.n_obs : 1;
   for (int o = 0; o < n_obs; ++o) {
     const unsigned lgrid = (unsigned)((a.B + 63) / 64);
