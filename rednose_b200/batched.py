@@ -58,7 +58,7 @@ class BatchedEKF:
     Qh = np.asarray(Q, dtype=np.float64) if not isinstance(Q, torch.Tensor) else Q.detach().cpu().numpy()
     if np.count_nonzero(Qh - np.diag(np.diagonal(Qh))) == 0:
       self.flags |= Q_IS_DIAGONAL  # lets the kernels skip the dense dt*Q read
-    self.kinds = sorted(int(s[len(name) + 12:]) for s in dir(self._lib) if s.startswith(f"{name}_batch_step_"))
+    self.kinds = sorted(int(s[len(name) + 12:]) for s in dir(self._lib) if s.startswith(f"{name}_batch_step_") and not s.endswith("_idx"))
     self._zdim = {}
     self.launches = 0  # kernels launched through this object (bench.py reports it)
     for g, v in (global_vars or {}).items():
@@ -123,6 +123,40 @@ class BatchedEKF:
         self._quat, self._nquat, flags, self._p(hx), self._p(hP), self._stream())
     self.launches += 1
     self._check(f"batch_update_{kind}")
+    return z
+
+  def step_indexed(self, kind, idx, dt, z, R, ea=None):
+    """Fused predict + update of `kind` for the filters listed in `idx` only ([n] int32, device): entry e uses
+    z[e], R[e] (or one shared R), dt[e] and works on filter idx[e].  Filters not listed are untouched.  This is the
+    building block of the ragged scheduler (per-tick kind buckets)."""
+    idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
+    n = int(idx.shape[0])
+    if n == 0:
+      return None
+    z = _as_device(z, self.device)
+    if z.ndim == 2:
+      z = z.unsqueeze(1)
+    R = _as_device(R, self.device)
+    flags = self.flags
+    if R.ndim == 2:
+      flags |= SHARED_R
+    elif R.ndim == 3:
+      R = R.unsqueeze(1)
+    assert z.shape[0] == n
+    ea = _as_device(ea, self.device) if ea is not None else None
+    if isinstance(dt, torch.Tensor):
+      dt = dt.to(self.device, torch.float64).contiguous()
+      assert dt.shape == (n,)
+      dt_ptr, dt_s = self._cp(dt), 0.0
+    else:
+      dt_ptr, dt_s = self._ffi.NULL, float(dt)
+    with torch.cuda.device(self.device):
+      getattr(self._lib, f"{self.name}_batch_step_{kind}_idx")(
+        self._p(self.x), self._p(self.P), self._cp(self.Q), dt_ptr, dt_s, self._p(z), self._cp(R), self._cp(ea),
+        z.shape[1], n, self._quat, self._nquat, flags, self._ffi.NULL, self._ffi.NULL, self._ffi.NULL, self._ffi.NULL,
+        self._ffi.cast("const int *", idx.data_ptr()), self._stream())
+    self.launches += 1
+    self._check(f"batch_step_{kind}_idx")
     return z
 
   def step(self, kind, dt, z, R, ea=None, hist_pred=None, hist_filt=None):

@@ -14,6 +14,7 @@
 #include "ekf_augment.cuh"
 #include <cstring>
 #include <mutex>
+#include <unordered_set>
 
 namespace rnb {
 
@@ -68,15 +69,28 @@ inline void launch_step(const StepArgs<M::NG>& a, cudaStream_t st) {
     }
     constexpr int G = RNB_GROUP, W = RNB_WARPS;
     constexpr size_t smem = warp_smem_bytes<M, K, G, W>();
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-      cudaFuncSetAttribute(ekf_step_warp<M, K, PRED, UPD, G, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(ekf_step_warp<M, K, PRED, UPD, G, W>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      configured = true;
-    }
     const long long per_cta = (long long)G * W;
     const unsigned grid = (unsigned)((a.B + per_cta - 1) / per_cta);
-    ekf_step_warp<M, K, PRED, UPD, G, W><<<grid, W * 32, smem, st>>>(a);
+    auto run = [&](void (*kern)(const StepArgs<M::NG>)) {
+      static std::unordered_set<const void*> configured;  // kernels share one pointer type: key by address
+      if (configured.insert((const void*)kern).second) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      }
+      kern<<<grid, W * 32, smem, st>>>(a);
+    };
+    if constexpr (PRED && UPD) {
+      // the gather-list variant exists only for the fused step (what the ragged scheduler issues)
+      if (a.idx) run(ekf_step_warp<M, K, PRED, UPD, G, W, true>);
+      else run(ekf_step_warp<M, K, PRED, UPD, G, W, false>);
+    } else {
+      if (a.idx) {
+        fprintf(stderr, "[rednose_b200] gather lists are only supported by the fused predict+update step\n");
+        last_status() = (int)cudaErrorNotSupported;
+        return;
+      }
+      run(ekf_step_warp<M, K, PRED, UPD, G, W, false>);
+    }
   } else {
     launch_step_cta<M, K, PRED, UPD>(a, st);
   }
@@ -110,9 +124,11 @@ template <class M, class K, bool PRED>
 inline void batch_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, const double* dt_arr, double dt,
                        double* z, const double* R, const double* ea, int n_obs, long long B,
                        const int* quat_idxs, int n_quat, int flags,
-                       double* hx_pred, double* hP_pred, double* hx_filt, double* hP_filt, void* stream) {
+                       double* hx_pred, double* hP_pred, double* hx_filt, double* hP_filt, void* stream,
+                       const int* idx = nullptr) {
   StepArgs<M::NG> a;
   fill_common<M>(a, ctx, B, quat_idxs, n_quat, flags);
+  a.idx = idx;
   a.x = x; a.P = P; a.Q = Q; a.dt_arr = dt_arr; a.dt = dt;
   a.z = z; a.R = R; a.ea = (K::EADIM > 0) ? ea : nullptr; a.ea_dim = K::EADIM; a.n_obs = n_obs;
   a.hx_pred = hx_pred; a.hP_pred = hP_pred; a.hx_filt = hx_filt; a.hP_filt = hP_filt;

@@ -35,7 +35,10 @@ struct StepArgs {
   const double* ea;      // [B, n_obs, EADIM] or nullptr
   int n_obs;
   int ea_dim;            // doubles of extra args per observation (0 if unused)
-  long long B;
+  long long B;           // number of ENTRIES processed by this launch
+  // optional gather list: entry e works on filter idx[e] of x / P / history, while z, R, ea, dt_arr stay
+  // entry-indexed (compact).  nullptr = entry e is filter e.  Used by the ragged scheduler (per-tick kind buckets).
+  const int* idx;
   int flags;
   int n_quat;
   int quat_idx[MAX_QUAT];

@@ -43,10 +43,11 @@ __global__ void __launch_bounds__(64) ekf_leaf_thread(const StepArgs<M::NG> a, i
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
   double* ws = ws_all + b * W::SIZE;
+  const long long fb = a.idx ? (long long)a.idx[b] : b;   // filter this entry works on
   double x[D];
   if (PRED || o == 0) {
 #pragma unroll
-    for (int i = 0; i < D; ++i) x[i] = a.x[b * D + i];
+    for (int i = 0; i < D; ++i) x[i] = a.x[fb * D + i];
   } else {
 #pragma unroll
     for (int i = 0; i < D; ++i) x[i] = ws[W::OFF_X + i];
@@ -68,11 +69,11 @@ __global__ void __launch_bounds__(64) ekf_leaf_thread(const StepArgs<M::NG> a, i
     for (int i = 0; i < D; ++i) x[i] = ws[W::OFF_X + i];
     if (a.hx_pred) {
 #pragma unroll
-      for (int i = 0; i < D; ++i) a.hx_pred[b * D + i] = x[i];
+      for (int i = 0; i < D; ++i) a.hx_pred[fb * D + i] = x[i];
     }
     if (!UPD) {
 #pragma unroll
-      for (int i = 0; i < D; ++i) a.x[b * D + i] = x[i];
+      for (int i = 0; i < D; ++i) a.x[fb * D + i] = x[i];
     }
   } else if (o == 0) {
 #pragma unroll
@@ -185,7 +186,8 @@ __global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS) ekf_step_cta(const 
   const int grp = tid / TPG, col = tid - grp * TPG;   // group 0 does the per-column work, all groups share the big row loops
   const long long b = blockIdx.x;
   const double* ws = ws_all + b * W::SIZE;
-  double* Pg = a.P + b * (long long)(E * E);
+  const long long fb = a.idx ? (long long)a.idx[b] : b;   // filter this entry works on
+  double* Pg = a.P + fb * (long long)(E * E);
   const bool own = col < E;            // this thread is attached to column `col`
   const bool own0 = own && grp == 0;   // ... and is the one that writes per-column results
 
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS) ekf_step_cta(const 
     }
     __syncthreads();
     if (a.hP_pred) {
-      double* Hg = a.hP_pred + b * (long long)(E * E);
+      double* Hg = a.hP_pred + fb * (long long)(E * E);
       for (int idx = tid; idx < E * E; idx += nth) Hg[idx] = s.P[(idx / E) * LD + idx % E];
     }
   }
@@ -407,14 +409,14 @@ __global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS) ekf_step_cta(const 
     }
     const bool last = (o == a.n_obs - 1);
     for (int i = tid; i < D; i += nth) {
-      if (last) a.x[b * D + i] = s.xo[i];
+      if (last) a.x[fb * D + i] = s.xo[i];
       const_cast<double*>(ws_all)[b * W::SIZE + W::OFF_X + i] = s.xo[i];  // next observation of this batch starts here
-      if (last && a.hx_filt) a.hx_filt[b * D + i] = s.xo[i];
+      if (last && a.hx_filt) a.hx_filt[fb * D + i] = s.xo[i];
     }
     // innovation overwrites z (ekf_c.c:120): the first YDIM entries
     for (int i = tid; i < Y; i += nth) a.z[(b * a.n_obs + o) * Z + i] = s.y[NR + i];
     if (last && a.hP_filt) {
-      double* Hg = a.hP_filt + b * (long long)(E * E);
+      double* Hg = a.hP_filt + fb * (long long)(E * E);
       for (int idx = tid; idx < E * E; idx += nth) Hg[idx] = s.P[(idx / E) * LD + idx % E];
     }
   }

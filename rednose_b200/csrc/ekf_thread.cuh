@@ -45,10 +45,11 @@ __global__ void __launch_bounds__(128) ekf_step_thread(const StepArgs<M::NG> a) 
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
 
+  const long long fb = a.idx ? (long long)a.idx[b] : b;   // filter this entry works on
   double x[D];
   double P[E * E];
-  load_rec<D>(a.x + b * D, x);
-  load_rec<E * E>(a.P + b * E * E, P);
+  load_rec<D>(a.x + fb * D, x);
+  load_rec<E * E>(a.P + fb * E * E, P);
 
   if constexpr (PRED) {
     const double dt = a.dt_arr ? a.dt_arr[b] : a.dt;
@@ -95,8 +96,8 @@ __global__ void __launch_bounds__(128) ekf_step_thread(const StepArgs<M::NG> a) 
 #pragma unroll
           for (int i = 0; i < D; ++i) if (i == a.quat_idx[q] + c) x[i] = qv[c];
       }
-    if (a.hx_pred) store_rec<D>(a.hx_pred + b * D, x);
-    if (a.hP_pred) store_rec<E * E>(a.hP_pred + b * E * E, P);
+    if (a.hx_pred) store_rec<D>(a.hx_pred + fb * D, x);
+    if (a.hP_pred) store_rec<E * E>(a.hP_pred + fb * E * E, P);
   }
 
   if constexpr (UPD) {
@@ -208,12 +209,12 @@ __global__ void __launch_bounds__(128) ekf_step_thread(const StepArgs<M::NG> a) 
 #pragma unroll
       for (int i = 0; i < Z; ++i) a.z[bo * Z + i] = y[i];
     }
-    if (a.hx_filt) store_rec<D>(a.hx_filt + b * D, x);
-    if (a.hP_filt) store_rec<E * E>(a.hP_filt + b * E * E, P);
+    if (a.hx_filt) store_rec<D>(a.hx_filt + fb * D, x);
+    if (a.hP_filt) store_rec<E * E>(a.hP_filt + fb * E * E, P);
   }
 
-  store_rec<D>(a.x + b * D, x);
-  store_rec<E * E>(a.P + b * E * E, P);
+  store_rec<D>(a.x + fb * D, x);
+  store_rec<E * E>(a.P + fb * E * E, P);
 }
 
 }  // namespace rnb

@@ -151,7 +151,29 @@ __device__ __forceinline__ void stage_out(double* __restrict__ g, const double* 
   }
 }
 
-template <class M, class K, bool PRED, bool UPD, int G, int W>
+// same for records scattered in global memory: record f lives at g + fid(f) * WD, fid held by lane f
+template <int WD, int STRIDE>
+__device__ __forceinline__ void gather_in(const double* __restrict__ g, double* rows, int off, int ng, int lane, long long myfid) {
+  for (int base = 0; base < ng * WD; base += 32) {
+    const int idx = base + lane;
+    const bool ok = idx < ng * WD;
+    const int f = ok ? idx / WD : 0, i = idx - f * WD;
+    const long long fid = __shfl_sync(0xffffffffu, myfid, f);
+    if (ok) rows[f * STRIDE + off + i] = g[fid * WD + i];
+  }
+}
+template <int WD, int STRIDE>
+__device__ __forceinline__ void scatter_out(double* __restrict__ g, const double* rows, int off, int ng, int lane, long long myfid) {
+  for (int base = 0; base < ng * WD; base += 32) {
+    const int idx = base + lane;
+    const bool ok = idx < ng * WD;
+    const int f = ok ? idx / WD : 0, i = idx - f * WD;
+    const long long fid = __shfl_sync(0xffffffffu, myfid, f);
+    if (ok) g[fid * WD + i] = rows[f * STRIDE + off + i];
+  }
+}
+
+template <class M, class K, bool PRED, bool UPD, int G, int W, bool GATHER>
 __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a) {
   constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM;
   using L = RowLayout<M, K>;
@@ -163,13 +185,22 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
   WarpScratch<M, K, G>& s = reinterpret_cast<WarpScratch<M, K, G>*>(smem_raw)[threadIdx.x >> 5];
 
   const int lane = threadIdx.x & 31;
-  const long long b0 = ((long long)blockIdx.x * W + (threadIdx.x >> 5)) * G;  // first filter of the group
+  const long long b0 = ((long long)blockIdx.x * W + (threadIdx.x >> 5)) * G;  // first ENTRY of the group
   if (b0 >= a.B) return;  // whole warp exits together
   const int ng = (a.B - b0 < G) ? (int)(a.B - b0) : G;
   const bool act = lane < E;
   const int col = act ? lane : 0;
   double* myrow = s.rows + (lane < G ? lane : 0) * RS;
   const bool mine = lane < ng;
+  // filter this lane's entry works on (gather list, ragged scheduler) -- entry index when there is no list
+  constexpr bool gathered = GATHER;
+  long long myfid = b0 + (mine ? lane : 0);
+  if constexpr (GATHER) { if (mine) myfid = (long long)a.idx[b0 + lane]; }
+  // filter id of entry f of the group: a shuffle only when a gather list is in use
+  auto fid_of = [&](int f) -> long long {
+    if constexpr (GATHER) return __shfl_sync(0xffffffffu, myfid, f);
+    else return b0 + f;
+  };
 
   constexpr bool TMA = use_tma<M>();
   constexpr int NST = TMA ? RNB_STAGES : 1;
@@ -185,9 +216,9 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
     __syncwarp();
   }
   // producer side of the tile ring: one elected lane arms the barrier and issues the bulk copy
-  auto issue_load = [&](int f, uint32_t slot) {
+  auto issue_load = [&](long long fid, uint32_t slot) {
     mbar_expect_tx(&s.full[slot], TILE_BYTES);
-    tma_load_1d(s.tile + slot * (E * E), a.P + (b0 + f) * (long long)(E * E), TILE_BYTES, &s.full[slot]);
+    tma_load_1d(s.tile + slot * (E * E), a.P + fid * (long long)(E * E), TILE_BYTES, &s.full[slot]);
   };
 
   // diagonal process noise: this lane's entry, fetched once per warp
@@ -206,14 +237,19 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
       // prefetch the first covariance tiles of the group; they land while the leaf phase runs
       if (lane == 0) {
         if (RNB_TMA_STORE) tma_store_wait_read();  // (o > 0) tiles of the previous pass must have drained
+      }
 #pragma unroll
-        for (int k = 0; k < NST - (RNB_TMA_STORE ? 1 : 0); ++k)
-          if (k < ng) issue_load(k, (it + k) % NST);
+      for (int k = 0; k < NST - (RNB_TMA_STORE ? 1 : 0); ++k) {
+        const long long fid = fid_of(k < ng ? k : 0);
+        if (lane == 0 && k < ng) issue_load(fid, (it + k) % NST);
       }
     }
 
     // ---- stage this group's small per-filter records into the rows (coalesced) ----
-    if (o == 0) stage_in<D, RS>(a.x + b0 * D, s.rows, L::OFF_X, ng, lane);
+    if (o == 0) {
+      if (gathered) gather_in<D, RS>(a.x, s.rows, L::OFF_X, ng, lane, myfid);
+      else stage_in<D, RS>(a.x + b0 * D, s.rows, L::OFF_X, ng, lane);
+    }
     if constexpr (UPD) {
       const bool shared_R = a.flags & FLAG_SHARED_R;
       if (a.n_obs == 1) {
@@ -264,7 +300,10 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
       }
     }
     __syncwarp();
-    if (do_pred && a.hx_pred) stage_out<D, RS>(a.hx_pred + b0 * D, s.rows, L::OFF_X, ng, lane);
+    if (do_pred && a.hx_pred) {
+      if (gathered) scatter_out<D, RS>(a.hx_pred, s.rows, L::OFF_X, ng, lane, myfid);
+      else stage_out<D, RS>(a.hx_pred + b0 * D, s.rows, L::OFF_X, ng, lane);
+    }
     if constexpr (UPD) {
       // the innovation overwrites z (ekf_c.c:120)
       if (a.n_obs == 1) {
@@ -279,7 +318,7 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
     // ================= phase B: covariance, one filter per warp iteration =================
 #pragma unroll 1
     for (int f = 0; f < ng; ++f) {
-      const long long b = b0 + f;
+      const long long b = fid_of(f);   // filter id of this iteration
       double* row = s.rows + f * RS;
       double p[E];
       const uint32_t slot = it % NST;
@@ -299,15 +338,17 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
         }
         if constexpr (RNB_TMA_STORE) {
           // tile f+NST-1 goes into the slot whose store was issued one iteration ago
+          const long long nfid = fid_of(f + NST - 1 < ng ? f + NST - 1 : 0);
           if (lane == 0 && f + NST - 1 < ng) {
             tma_store_wait_read();
-            issue_load(f + NST - 1, (it + NST - 1) % NST);
+            issue_load(nfid, (it + NST - 1) % NST);
           }
         } else {
           // the slot is free as soon as every lane has its column in registers: refill it at once,
           // keeping NST bulk loads in flight per warp
-          __syncwarp();
-          if (lane == 0 && f + NST < ng) issue_load(f + NST, slot);
+          const long long nfid = fid_of(f + NST < ng ? f + NST : 0);
+          __syncwarp();   // every lane has read its column before the slot is overwritten
+          if (lane == 0 && f + NST < ng) issue_load(nfid, slot);
         }
       } else {
         const double* Pg = a.P + b * (long long)(E * E) + col;
@@ -465,8 +506,12 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
       __syncwarp();
     }
     if (o == n_obs - 1) {
-      stage_out<D, RS>(a.x + b0 * D, s.rows, L::OFF_X, ng, lane);
-      if (UPD && a.hx_filt) stage_out<D, RS>(a.hx_filt + b0 * D, s.rows, L::OFF_X, ng, lane);
+      if (gathered) scatter_out<D, RS>(a.x, s.rows, L::OFF_X, ng, lane, myfid);
+      else stage_out<D, RS>(a.x + b0 * D, s.rows, L::OFF_X, ng, lane);
+      if (UPD && a.hx_filt) {
+        if (gathered) scatter_out<D, RS>(a.hx_filt, s.rows, L::OFF_X, ng, lane, myfid);
+        else stage_out<D, RS>(a.hx_filt + b0 * D, s.rows, L::OFF_X, ng, lane);
+      }
     }
     __syncwarp();
   }

@@ -297,3 +297,42 @@ def test_host_streamer_equals_direct_stepping(gen_dir):
   xh, yh = st.result(tickets[-1], zs[-1][0])
   assert torch.equal(xh, want[-1][0]) and torch.equal(yh, want[-1][1])
   assert torch.equal(a.P, b.P)
+
+
+def test_ragged_scheduler_matches_per_filter_driving(gen_dir, oracle_dir):
+  """Every filter gets its own observation stream (different kinds, different times, gaps); the scheduler's
+  bucketed indexed launches must equal driving each filter on its own (oracle predict + update per observation)."""
+  from rednose_b200.scheduler import RaggedScheduler
+  o = Oracle(oracle_dir, "live")
+  B, ticks = 301, 12
+  x, P, Qm = live_batch(B, seed=123)
+  e = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  sch = RaggedScheduler(e)
+  rng = np.random.default_rng(7)
+  xr, Pr = x.copy(), P.copy()
+  t_ref = np.full(B, np.nan)
+  kinds_all = [4, 10, 12, 3]
+  for tick in range(ticks):
+    active = np.flatnonzero(rng.random(B) < 0.6)                   # ~40 % of the filters see nothing this tick
+    t_obs = 0.01 * (tick + 1) + rng.uniform(0, 0.004, active.size)  # per-filter observation times
+    kinds = rng.choice(kinds_all, active.size)
+    zs, Rs = {}, {}
+    for k in kinds_all:
+      sel = active[kinds == k]
+      if sel.size == 0:
+        continue
+      zk, Rk = live_obs(o, k, xr[sel], seed=1000 + tick)
+      zs[k], Rs[k] = zk, Rk
+      # reference: drive each selected filter on its own
+      dt = np.where(np.isnan(t_ref[sel]), 0.0, t_obs[kinds == k] - t_ref[sel])
+      xs, Ps, _ = o.batch_step(k, xr[sel], Pr[sel], Qm, dt, zk, Rk, quat_idxs=[3], flags=3)
+      xr[sel], Pr[sel] = xs, Ps
+      t_ref[sel] = t_obs[kinds == k]
+    sch.tick(active, t_obs, kinds, zs, Rs)
+  assert sch.dropped == 0
+  assert rel_err(e.state(), xr) < TIGHT and rel_err(e.covs(), Pr) < TIGHT
+  assert np.allclose(sch.t_filter.cpu().numpy(), t_ref, equal_nan=True)
+  # a late observation is dropped, not applied
+  before = e.state().copy()
+  sch.tick(np.array([0]), np.array([1e-6]), np.array([12]), {12: x[:1, 0:3]}, {12: np.diag([25.0] * 3)})
+  assert sch.dropped == 1 and np.array_equal(before, e.state())
