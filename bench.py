@@ -378,6 +378,36 @@ def run_extras(dev, peak):
                               "GBps_algorithmic": 12176 * B / (bwd_ms * 1e-3) / 1e9, "frac_of_peak": 12176 * B / (bwd_ms * 1e-3) / 1e9 / peak,
                               "finite": bool(torch.isfinite(xs).all() and torch.isfinite(Ps).all())}
   del e, hist, xs, Ps
+  # ragged streams: every tick ~60 % of 1M live filters see one observation of kind 4 / 10 / 12, the rest nothing
+  try:
+    from rednose_b200.scheduler import RaggedScheduler
+    B = 1 << 20
+    x0, P0, Q, pools, _, quat = make_problem("live", B, 13, d)
+    e = BatchedEKF(d, "live", Q, x0, P0, device=dev, quaternion_idxs=quat)
+    sch = RaggedScheduler(e)
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    ticks = []
+    for tk in range(6):
+      act = (torch.rand(B, device=dev, generator=g) < 0.6).nonzero(as_tuple=True)[0]
+      kk = torch.tensor([4, 10, 12], device=dev)[torch.randint(0, 3, (act.numel(),), device=dev, generator=g)]
+      zs = {k: torch.as_tensor(pools[k][0][0]).to(dev)[act[kk == k]] for k in (4, 10, 12)}
+      ticks.append((act, 0.01 * (tk + 1), kk, zs))
+    Rs = {k: torch.as_tensor(pools[k][1][0]).to(dev) for k in (4, 10, 12)}
+    sch.tick(ticks[0][0], ticks[0][1], ticks[0][2], ticks[0][3], Rs)   # warm-up
+    torch.cuda.synchronize(dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    t0.record()
+    for act, tt, kk, zs in ticks[1:]:
+      sch.tick(act, tt, kk, zs, Rs)
+      n += act.numel()
+    t1.record(); torch.cuda.synchronize(dev)
+    ms = t0.elapsed_time(t1)
+    out["live_ragged_scheduler"] = {"filters": B, "ticks": len(ticks) - 1, "observations": n, "steps_per_s": n / (ms * 1e-3),
+                                    "note": "bucketing by kind (torch index ops) + 3 indexed fused launches per tick", "finite": bool(torch.isfinite(e.x).all())}
+    del e, sch, ticks
+  except Exception as ex:  # pylint: disable=broad-except
+    out["live_ragged_scheduler"] = {"error": repr(ex)[:200]}
   # MSCKF 10k: fused predict + feature-track update (null-space projection + gate), CTA-per-filter
   try:
     from rednose_b200.ekf_sym import EKF_sym
@@ -477,27 +507,52 @@ def _cpu_problem(fname, B):
 
 
 def run_reference(args):
+  """Reference arm: the reference's C path (oracle/_ref) on the host cores, same workload / metric / unit.
+  The synthetic problem is built once; every step is one bounded pass (a few predict+update sub-steps of the
+  workload's kind schedule over a fixed sample of filters) sized so that warm-up + K steps take about two minutes."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
+  from oracle import build_ref
+  from oracle.handle import Oracle
   wl = WORKLOADS[args.workload]
   fname = wl["filter"]
   dim, edim = (2, 2) if fname == "kinematic" else (23, 22)
-  # each "step" is a bounded sample; K steps + W warmup must end within a few minutes
-  budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))
-  res = None
-  vals = []
+  if build_ref.reference_available():
+    build_ref.build(fname)
+  o = Oracle(build_ref.OUT, fname)
+  cores = os.cpu_count() or 1
+  sched = kind_schedule(fname, 4096)
+  # calibrate on a small sample
+  x, P, Q, pools, _, quat = _cpu_problem(fname, 2048)
+  t = time.perf_counter()
+  k = sched[1]
+  o.batch_step(k, x, P, Q, 0.01, pools[k][0][0], pools[k][1], quat_idxs=quat, flags=3, nthreads=cores)
+  per = max((time.perf_counter() - t) / 2048, 1e-9)
+  n_sub = 4
+  total_budget = 110.0
+  Bs = int(max(cores * 8, min(400_000, total_budget / (args.steps + args.warmup) / (per * n_sub))))
+  x, P, Q, pools, _, quat = _cpu_problem(fname, Bs)
+  times, it = [], 0
   for i in range(args.warmup + args.steps):
-    res = cpu_reference(fname, args.workload, budget_s=budget, steps=10)
+    t = time.perf_counter()
+    for _ in range(n_sub):
+      k = sched[it]
+      zp, R = pools[k]
+      x, P, _y = o.batch_step(k, x, P, Q, 0.01, zp[it % zp.shape[0]], R, quat_idxs=quat, flags=3, nthreads=cores)
+      it += 1
     if i >= args.warmup:
-      vals.append(res["value"])
-  v = float(np.mean(vals))
-  res["value"] = v
+      times.append(time.perf_counter() - t)
+  assert np.isfinite(x).all()
+  v = Bs * n_sub / float(np.mean(times))
+  cb = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+        "sample": f"{Bs} {fname} filters x {n_sub} sub-steps per step, {args.steps} timed steps, workload {args.workload} kind schedule",
+        "what": "reference-generated leaf C (rednose gen_code, unmodified) + Eigen-free restatement of ekf_c.c, g++ -O2, threads over filters"}
   line = {"impl": "reference", "metric": "fused EKF predict+update steps/s (batched, float64)", "value": v, "unit": "steps/s",
-          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True,
           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-          "config": {"workload": args.workload, "filter": fname, "dim": dim, "edim": edim},
-          "cpu_baseline": res,
+          "config": {"workload": args.workload, "filter": fname, "dim": dim, "edim": edim, "sample_filters": Bs},
+          "cpu_baseline": cb,
           "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
   print(json.dumps(line))
 
@@ -513,7 +568,9 @@ def main():
   ap.add_argument("--e2e-steps", type=int, default=20)
   ap.add_argument("--cpu-budget", type=float, default=15.0)
   ap.add_argument("--no-cpu-baseline", action="store_true")
-  ap.add_argument("--extras", action="store_true", help="also time the kinematic / RTS / history / MSCKF kernels (adds ~1 min)")
+  ap.add_argument("--no-extras", dest="extras", action="store_false",
+                  help="skip the short measurements of the other kernels (kinematic / history / RTS / ragged / MSCKF, ~1 min)")
+  ap.add_argument("--extras", dest="extras", action="store_true", default=True)
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3)
   if args.impl == "reference":
