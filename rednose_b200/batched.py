@@ -224,7 +224,7 @@ class BatchedEKF:
     hist.n += 1
     return y
 
-  def rts_smooth(self, hist, norm_quats=False, quaternion_idxs=(3,), in_place=False):
+  def rts_smooth(self, hist, norm_quats=False, quaternion_idxs=(3,), in_place=False, out=None):
     """Batched RTS backward pass over a recorded history (ekf_sym.py:651-690, one launch for all filters).
 
     Returns (xs [T, B, DIM], Ps [T, B, EDIM, EDIM]) on the device.  `norm_quats` normalises the quaternion(s)
@@ -232,8 +232,11 @@ class BatchedEKF:
     """
     T = hist.n
     assert T >= 1
-    xs = hist.x_filt if in_place else torch.empty_like(hist.x_filt)
-    Ps = hist.P_filt if in_place else torch.empty_like(hist.P_filt)
+    if out is not None:
+      xs, Ps = out                      # caller-provided [T, B, DIM] / [T, B, EDIM, EDIM] buffers
+    else:
+      xs = hist.x_filt if in_place else torch.empty_like(hist.x_filt)
+      Ps = hist.P_filt if in_place else torch.empty_like(hist.P_filt)
     qi = self._ffi.new("int[]", list(quaternion_idxs) or [0])
     with torch.cuda.device(self.device):
       getattr(self._lib, f"{self.name}_batch_rts")(
