@@ -109,7 +109,7 @@ def make_problem(filter_name, B, seed, lib_dir):
   if filter_name == "kinematic":
     from rednose_b200.filters.kinematic import KinematicKalman as F
     x = np.tile(F.initial_x, (B, 1)) + rng.normal(size=(B, 2))
-    P = np.tile(np.diag(F.initial_P_diag), (B, 1, 1))
+    P = np.diag(F.initial_P_diag)
     pools = {1: (rng.normal(0.0, 0.1, (4, B, 1)), np.tile(np.array([[0.1**2]]), (B, 1, 1)))}
     return x, P, F.Q.copy(), pools, (2, 2), []
   from rednose_b200.ekf_sym import EKF_sym
@@ -124,7 +124,7 @@ def make_problem(filter_name, B, seed, lib_dir):
   x[:, 10:13] += rng.normal(0, 0.05, (B, 3))
   x[:, 17:20] += rng.normal(0, 0.3, (B, 3))
   pdiag = np.array([25.0] * 3 + [0.05**2] * 3 + [1.0] * 3 + [0.1**2] * 3 + [0.01**2] * 3 + [0.01**2] + [0.5**2] * 3 + [0.01**2] * 3)
-  P = np.tile(np.diag(pdiag), (B, 1, 1))
+  P = np.diag(pdiag)   # one covariance, broadcast to the batch on the device
   pools = {}
   for k, rdiag in LIVE_R.items():
     hz = np.zeros(3)

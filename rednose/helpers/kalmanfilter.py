@@ -1,1 +1,1 @@
-from rednose_b200.kalmanfilter import KalmanFilter  # noqa: F401
+from rednose_b200.filter_base import KalmanFilter  # noqa: F401

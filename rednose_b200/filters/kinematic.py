@@ -8,7 +8,7 @@ import sys
 
 import numpy as np
 
-from rednose_b200.kalmanfilter import KalmanFilter
+from rednose_b200.filter_base import KalmanFilter
 
 
 class ObservationKind:

@@ -336,3 +336,18 @@ def test_ragged_scheduler_matches_per_filter_driving(gen_dir, oracle_dir):
   before = e.state().copy()
   sch.tick(np.array([0]), np.array([1e-6]), np.array([12]), {12: x[:1, 0:3]}, {12: np.diag([25.0] * 3)})
   assert sch.dropped == 1 and np.array_equal(before, e.state())
+
+
+def test_edge_batches_empty_single_and_ragged_tail(gen_dir, oracle_dir):
+  """B = 0 (no launch, no error), B = 1, and a batch one short / one over a multiple of the warp group."""
+  o = Oracle(oracle_dir, "live")
+  for B in (0, 1, 13, 15, 29):
+    x, P, Qm = live_batch(max(B, 1), seed=200 + B)
+    x, P = x[:B], P[:B]
+    z, R = (live_obs(o, 12, x) if B else (np.zeros((0, 3)), np.zeros((0, 3, 3))))
+    e = _engine(gen_dir, "live", x if B else np.zeros((0, 23)), P if B else np.zeros((0, 22, 22)), Qm, quaternion_idxs=[3])
+    y = e.step(12, 0.01, z, R)
+    assert y.shape[0] == B
+    if B:
+      xr, Pr, yr = o.batch_step(12, x, P, Qm, 0.01, z, R, quat_idxs=[3], flags=3)
+      assert rel_err(e.state(), xr) < TIGHT and rel_err(e.covs(), Pr) < TIGHT

@@ -34,3 +34,31 @@ def test_driver_state_views_and_time(oracle_dir):
     raise AssertionError("unknown kind must raise")
   except KeyError:
     pass
+
+
+def test_runtime_exports_every_symbol_declared_in_the_public_header():
+  """include/rednose_b200.h: every function prototype must resolve in librednose_b200.so."""
+  import re
+  from rednose_b200.build import INCLUDE_DIR
+  rt = runtime()
+  with open(f"{INCLUDE_DIR}/rednose_b200.h", encoding="utf-8") as f:
+    text = f.read()
+  names = re.findall(r"^(?:void|int|double|const rednose_ekf_desc) \*?(rednose_\w+)\(", text, flags=re.M)
+  assert len(names) >= 18, names
+  for n in names:
+    assert hasattr(rt, n), n
+
+
+def test_product_fails_loudly_without_a_gpu(gen_dir):
+  """No CPU fallback: on a box without CUDA the single-filter C-ABI latches a CUDA error and the binding raises."""
+  import pytest
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("a GPU is present")
+  from rednose_b200.ekf_sym import EKF_sym
+  from rednose_b200.batched import BatchedEKF
+  kf = EKF_sym(gen_dir, "kinematic", np.diag([0.01, 4.0]), np.array([0.5, 0.0]), np.eye(2), 2, 2)
+  with pytest.raises(RuntimeError, match="CUDA error"):
+    kf.predict_and_update_batch(0.0, 1, np.array([[0.1]]), np.array([[[0.01]]]))
+  with pytest.raises(RuntimeError, match="no CPU fallback"):
+    BatchedEKF(gen_dir, "kinematic", np.diag([0.01, 4.0]), np.array([0.5, 0.0]), np.eye(2), batch=4)
