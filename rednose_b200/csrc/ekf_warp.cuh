@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
         vec_load(row + L::OFF_Y, y);
         vec_load(row + L::OFF_R, R);
 
-        LDL<Z> ldl;
+        SolverZ<Z> ldl;
         if constexpr (K::MAHA) {
           double Sg[Z][Z];
 #pragma unroll
