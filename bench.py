@@ -378,6 +378,34 @@ def run_extras(dev, peak):
                               "GBps_algorithmic": 12176 * B / (bwd_ms * 1e-3) / 1e9, "frac_of_peak": 12176 * B / (bwd_ms * 1e-3) / 1e9 / peak,
                               "finite": bool(torch.isfinite(xs).all() and torch.isfinite(Ps).all())}
   del e, hist, xs, Ps
+  # config 4 in miniature: forward + RTS over a history that is tiled over filters (history = 8.1 kB per filter-step)
+  try:
+    from rednose_b200.smoothing import TiledSmoother
+    B, T, tile = 32768, 32, 8192
+    x0, P0, Q, pools, _, quat = make_problem("live", B, 17, d)
+    P0 = np.broadcast_to(P0, (B, 22, 22))
+    x0d, P0d = torch.as_tensor(x0).to(dev), torch.as_tensor(np.ascontiguousarray(P0)).to(dev)
+    zp = {k: torch.as_tensor(v[0][0]).to(dev) for k, v in pools.items()}
+    Rk = {k: torch.as_tensor(v[1][0]).to(dev) for k, v in pools.items()}
+    sched = kind_schedule("live", T)
+    acc = {"n": 0}
+    def obs_fn(k, lo, hi):
+      return 0.01 * (k + 1), sched[k], zp[sched[k]][lo:hi].clone(), Rk[sched[k]]
+    def sink(lo, hi, xs, Ps):
+      acc["n"] += int(torch.isfinite(xs).all())
+    ts = TiledSmoother(d, "live", Q, 23, 22, quaternion_idxs=quat, device=dev, tile=tile)
+    ts.run(x0d[:tile], P0d[:tile], T, obs_fn, sink, norm_quats=True)   # warm-up: allocations
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    ntiles = ts.run(x0d, P0d, T, obs_fn, sink, norm_quats=True)
+    torch.cuda.synchronize(dev)
+    el = time.perf_counter() - t0
+    out["live_tiled_forward_plus_rts"] = {"filters": B, "T": T, "tile": tile, "tiles": ntiles, "seconds": el,
+                                          "filter_steps_per_s": B * T / el, "finite_tiles": acc["n"],
+                                          "note": "forward with history + backward RTS per tile, smoothed track handed to a sink; config 4 (1M x 10k over 8 GPUs) = 125k filters/GPU in tiles of ~1.8k"}
+    del ts, x0d, P0d
+  except Exception as ex:  # pylint: disable=broad-except
+    out["live_tiled_forward_plus_rts"] = {"error": repr(ex)[:200]}
   # ragged streams: every tick ~60 % of 1M live filters see one observation of kind 4 / 10 / 12, the rest nothing
   try:
     from rednose_b200.scheduler import RaggedScheduler

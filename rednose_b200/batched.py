@@ -39,8 +39,8 @@ class BatchedEKF:
     self._ffi, self._lib = load_code(folder, name)
     ffi = self._ffi
     # single states / covariances are broadcast ON THE DEVICE (a 1M x 22 x 22 tile is 3.9 GB: never built on the host)
-    x0 = torch.as_tensor(np.asarray(x_initial, dtype=np.float64)).to(self.device)
-    P0 = torch.as_tensor(np.asarray(P_initial, dtype=np.float64)).to(self.device)
+    x0 = _as_device(x_initial, self.device)
+    P0 = _as_device(P_initial, self.device)
     if x0.ndim == 1:
       assert batch is not None, "batch size needed when broadcasting a single initial state"
       x0 = x0.expand(batch, -1)

@@ -351,3 +351,29 @@ def test_edge_batches_empty_single_and_ragged_tail(gen_dir, oracle_dir):
     if B:
       xr, Pr, yr = o.batch_step(12, x, P, Qm, 0.01, z, R, quat_idxs=[3], flags=3)
       assert rel_err(e.state(), xr) < TIGHT and rel_err(e.covs(), Pr) < TIGHT
+
+
+def test_tiled_smoother_equals_untiled(gen_dir, oracle_dir):
+  """Config 4 in miniature: forward + RTS over a history, tiled over filters because the history does not fit."""
+  from rednose_b200.smoothing import TiledSmoother, history_bytes_per_filter
+  o = Oracle(oracle_dir, "live")
+  B, T = 37, 12
+  x, P, Qm = live_batch(B, seed=300)
+  kinds = [12 if k % 5 == 0 else 4 for k in range(T)]
+  zs = [live_obs(o, kinds[k], x, seed=400 + k) for k in range(T)]
+
+  def obs_fn(k, lo, hi):
+    return 0.01 * (k + 1), kinds[k], zs[k][0][lo:hi], zs[k][1][lo:hi]
+
+  got = {}
+  def sink(lo, hi, xs, Ps):
+    got[(lo, hi)] = (xs.cpu().numpy().copy(), Ps.cpu().numpy().copy())
+
+  assert history_bytes_per_filter(23, 22, 10_000) == 8 * (2 * 484 + 46) * 10_000   # 81 MB per live filter over 10k steps
+  ts = TiledSmoother(gen_dir, "live", Qm, 23, 22, quaternion_idxs=[3], tile=16)
+  assert ts.run(x, P, T, obs_fn, sink, norm_quats=True) == 3
+  ref = {}
+  TiledSmoother(gen_dir, "live", Qm, 23, 22, quaternion_idxs=[3], tile=64).run(x, P, T, obs_fn, lambda lo, hi, xs, Ps: ref.update(a=(xs.cpu().numpy().copy(), Ps.cpu().numpy().copy())), norm_quats=True)
+  xs_t = np.concatenate([got[k][0] for k in sorted(got)], axis=1)
+  Ps_t = np.concatenate([got[k][1] for k in sorted(got)], axis=1)
+  assert np.array_equal(xs_t, ref["a"][0]) and np.array_equal(Ps_t, ref["a"][1])
