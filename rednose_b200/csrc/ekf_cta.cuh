@@ -388,8 +388,25 @@ __global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS) ekf_step_cta(const 
       // P[:, col] -= HP^T w; the groups split the rows
       constexpr int RPG = (E + CTA_GROUPS - 1) / CTA_GROUPS;
       const int i0 = grp * RPG, i1 = (i0 + RPG < E) ? i0 + RPG : E;
-#pragma unroll 2
-      for (int i = i0; i < i1; ++i) {
+      // four rows at a time: four independent accumulation chains hide the FP64 latency
+      int i = i0;
+      for (; i + 4 <= i1; i += 4) {
+        double acc[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = s.P[(i + r) * LD + col];
+#pragma unroll
+        for (int c = 0; c < Y; c += 2) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const double2 h2 = *reinterpret_cast<const double2*>(&s.HP[(i + r) * HL + c]);
+            acc[r] = fma(-h2.x, w[c], acc[r]);
+            if (c + 1 < Y) acc[r] = fma(-h2.y, w[c + 1], acc[r]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s.P[(i + r) * LD + col] = acc[r];
+      }
+      for (; i < i1; ++i) {
         double acc = s.P[i * LD + col];
 #pragma unroll
         for (int c = 0; c < Y; c += 2) {
