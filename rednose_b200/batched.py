@@ -199,6 +199,27 @@ class BatchedEKF:
     self.P.copy_(_as_device(P, self.device).expand_as(self.P))
     self.filter_time = filter_time
 
+  def maha_dist(self, kind, z, R, ea=None):
+    """Mahalanobis distance y^T (H P H^T + R)^-1 y of one observation per filter, without touching the state
+    (the quantity EKF_sym.maha_test thresholds, ekf_sym.py:626-649).  Returns a [B] device tensor."""
+    z = _as_device(z, self.device).reshape(self.B, -1).contiguous()
+    R = _as_device(R, self.device)
+    flags = SHARED_R if R.ndim == 2 else 0
+    ea = _as_device(ea, self.device) if ea is not None else None
+    out = torch.empty(self.B, dtype=torch.float64, device=self.device)
+    with torch.cuda.device(self.device):
+      getattr(self._lib, f"{self.name}_batch_maha_{kind}")(
+        self._cp(self.x), self._cp(self.P), self._cp(z), self._cp(R), self._cp(ea), self.B, flags, self._p(out), self._stream())
+    self.launches += 1
+    self._check(f"batch_maha_{kind}")
+    return out
+
+  def maha_test(self, kind, z, R, ea=None, maha_thresh=0.95):
+    """True where the observation passes the chi-square gate at `maha_thresh` (batched EKF_sym.maha_test)."""
+    from rednose_b200.chi2 import chi2_ppf
+    d = self.maha_dist(kind, z, R, ea)
+    return d <= float(chi2_ppf(maha_thresh, z.shape[-1] if hasattr(z, "shape") else len(z[0])))
+
   def augment(self):
     """MSCKF clone window shift for the whole batch (ekf_sym.py:365-391), one launch."""
     with torch.cuda.device(self.device):

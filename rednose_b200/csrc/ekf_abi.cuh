@@ -135,6 +135,28 @@ inline void batch_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, c
   launch_step<M, K, PRED, true>(a, (cudaStream_t)stream);
 }
 
+}  // namespace rnb
+#include "ekf_maha.cuh"
+namespace rnb {
+
+// Mahalanobis distances of B observations of one kind (ekf_sym.py:626-649); out [B] on the device
+template <class M, class K>
+inline void batch_maha(HostCtx<M>& ctx, const double* x, const double* P, const double* z, const double* R, const double* ea,
+                       long long B, int flags, double* out, void* stream) {
+  if (B <= 0) return;
+  static double* scratch = nullptr;
+  static size_t cap = 0;
+  const size_t need = (size_t)B * K::ZDIM * M::EDIM;
+  if (need > cap) {
+    if (scratch) cudaFree(scratch);
+    scratch = nullptr; cap = 0;
+    if (!check(cudaMalloc(&scratch, need * sizeof(double)), "cudaMalloc(maha scratch)")) return;
+    cap = need;
+  }
+  ekf_maha_thread<M, K><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, P, z, R, ea, B, flags, ctx.gv, out, scratch);
+  check(cudaGetLastError(), "ekf_maha launch");
+}
+
 template <class M>
 inline void batch_rts(HostCtx<M>& ctx, const double* hx_pred, const double* hP_pred, const double* hx_filt, const double* hP_filt,
                       const double* t, int t_per_filter, double* xs, double* Ps, int T, long long B,

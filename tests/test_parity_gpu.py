@@ -377,3 +377,51 @@ def test_tiled_smoother_equals_untiled(gen_dir, oracle_dir):
   xs_t = np.concatenate([got[k][0] for k in sorted(got)], axis=1)
   Ps_t = np.concatenate([got[k][1] for k in sorted(got)], axis=1)
   assert np.array_equal(xs_t, ref["a"][0]) and np.array_equal(Ps_t, ref["a"][1])
+
+
+def test_batched_maha_query_matches_reference_formula(gen_dir, oracle_dir):
+  """(f)-2: batched maha_test vs ekf_sym.py:626-649 written out with the oracle's leaf functions."""
+  o = Oracle(oracle_dir, "live")
+  B = 211
+  x, P, Qm = live_batch(B, seed=500)
+  for kind, m in ((4, 3), (3, 1), (12, 3)):
+    z, R = live_obs(o, kind, x, seed=600 + kind, noise_scale=3.0)
+    e = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+    d = e.maha_dist(kind, z, R).cpu().numpy()
+    want = np.zeros(B)
+    dummy = np.zeros(1)
+    for b in range(B):
+      xb = np.ascontiguousarray(x[b])
+      h, H, Hm = np.zeros(m), np.zeros(m * 23), np.zeros(23 * 22)
+      o.leaf(f"h_{kind}", xb, dummy, h); o.leaf(f"H_{kind}", xb, dummy, H); o.leaf("H_mod_fun", xb, Hm)
+      He = H.reshape(m, 23) @ Hm.reshape(23, 22)
+      y = z[b] - h
+      want[b] = y @ np.linalg.inv(He @ P[b] @ He.T + R[b]) @ y
+    assert rel_err(d, want) < 1e-9, kind
+    assert torch.equal(e.x.cpu(), torch.as_tensor(x))   # a query: state untouched
+    passed = e.maha_test(kind, z, R).cpu().numpy()
+    from rednose_b200.chi2 import chi2_ppf
+    assert np.array_equal(passed, want <= chi2_ppf(0.95, m))
+
+
+def test_batched_kalmanfilter_front_end(gen_dir, oracle_dir):
+  """(f)-2: KalmanFilter.predict_and_observe for a whole batch (shared per-kind noise from obs_noise)."""
+  from rednose_b200.filter_base import BatchedKalmanFilter
+  from rednose_b200.filters.kinematic import KinematicKalman
+  o = Oracle(oracle_dir, "kinematic")
+  B = 1000
+  x, P, Qm, z, R = kinematic_batch(B, seed=9)
+
+  class BatchedKinematic(BatchedKalmanFilter):
+    obs_noise = KinematicKalman.obs_noise
+
+    def __init__(self):
+      self.filter = _engine(gen_dir, "kinematic", Qm, x, P)
+
+  kf = BatchedKinematic()
+  kf.predict_and_observe(0.0, 1, z)
+  kf.predict_and_observe(0.05, 1, z)
+  xr, Pr, _ = o.batch_step(1, x, P, Qm, 0.0, z, R)
+  xr, Pr, _ = o.batch_step(1, xr, Pr, Qm, 0.05, z, R)
+  assert rel_err(kf.x, xr) < TIGHT and rel_err(kf.P, Pr) < TIGHT and kf.t == 0.05
+  assert kf.maha_test(1, z).shape == (B,)
