@@ -45,7 +45,7 @@ def compile_filter(folder, name, force=False, verbose=False):
   lib = os.path.join(folder, f"lib{name}.so")
   if not force and _newer(lib, [src] + csrc_sources()):
     return lib
-  tune = [f"-D{k}={os.environ[e]}" for k, e in (("RNB_GROUP", "REDNOSE_B200_GROUP"), ("RNB_WARPS", "REDNOSE_B200_WARPS"), ("RNB_TMA", "REDNOSE_B200_TMA"), ("RNB_STAGES", "REDNOSE_B200_STAGES"), ("RNB_TMA_STORE", "REDNOSE_B200_TMA_STORE"), ("RNB_SMALLSYM", "REDNOSE_B200_SMALLSYM")) if os.environ.get(e)]
+  tune = [f"-D{k}={os.environ[e]}" for k, e in (("RNB_GROUP", "REDNOSE_B200_GROUP"), ("RNB_WARPS", "REDNOSE_B200_WARPS"), ("RNB_TMA", "REDNOSE_B200_TMA"), ("RNB_STAGES", "REDNOSE_B200_STAGES"), ("RNB_TMA_STORE", "REDNOSE_B200_TMA_STORE"), ("RNB_SMALLSYM", "REDNOSE_B200_SMALLSYM"), ("RNB_STAGE_BATCHED", "REDNOSE_B200_STAGE_BATCHED")) if os.environ.get(e)]
   if os.environ.get("REDNOSE_B200_MAXRREG"):
     tune += ["-maxrregcount", os.environ["REDNOSE_B200_MAXRREG"]]
   cmd = [nvcc_path()] + NVCC_FLAGS + tune + ["-Xptxas", "-v", f"-I{CSRC_DIR}", f"-I{INCLUDE_DIR}", "-o", lib, src]

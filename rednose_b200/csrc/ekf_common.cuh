@@ -143,7 +143,7 @@ struct SmallSym<3> {
 };
 
 #ifndef RNB_SMALLSYM
-#define RNB_SMALLSYM 1
+#define RNB_SMALLSYM 0   // 1 = closed-form adjugate inverse for Z <= 3: ~1 % faster, ~10x larger rounding error on ill-conditioned S; off
 #endif
 #if RNB_SMALLSYM
 template <int Z> using SolverZ = SmallSym<Z>;

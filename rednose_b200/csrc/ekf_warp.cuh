@@ -38,6 +38,9 @@ namespace rnb {
 #define RNB_WARPS 1    // warps per CTA (warps never synchronise with each other)
 #endif
 
+#ifndef RNB_STAGE_BATCHED
+#define RNB_STAGE_BATCHED 1   // staging of x / z / R: issue every load of the block before the first store
+#endif
 #ifndef RNB_TMA
 #define RNB_TMA 1      // stage covariance tiles through shared memory with cp.async.bulk (TMA) load + store
 #endif
@@ -136,11 +139,28 @@ __device__ __forceinline__ void lane_normalize(double* xs, const StepArgs<NG>& a
 
 // cooperative, coalesced copy between a contiguous global block of ng records of width WD and the
 // per-filter rows in shared memory (record f -> rows[f * STRIDE + off .. + WD))
-template <int WD, int STRIDE>
+template <int WD, int STRIDE, int G>
 __device__ __forceinline__ void stage_in(const double* __restrict__ g, double* rows, int off, int ng, int lane) {
+  // all loads first, then all stores: one global-latency round trip for the whole block instead of one per pass
+#if !RNB_STAGE_BATCHED
   for (int idx = lane; idx < ng * WD; idx += 32) {
     const int f = idx / WD, i = idx - f * WD;
     rows[f * STRIDE + off + i] = g[idx];
+  }
+  return;
+#endif
+  constexpr int NIT = (G * WD + 31) / 32;
+  double v[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = it * 32 + lane;
+    v[it] = (idx < ng * WD) ? g[idx] : 0.0;
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = it * 32 + lane;
+    const int f = idx / WD, i = idx - f * WD;
+    if (idx < ng * WD) rows[f * STRIDE + off + i] = v[it];
   }
 }
 template <int WD, int STRIDE>
@@ -152,14 +172,23 @@ __device__ __forceinline__ void stage_out(double* __restrict__ g, const double* 
 }
 
 // same for records scattered in global memory: record f lives at g + fid(f) * WD, fid held by lane f
-template <int WD, int STRIDE>
+template <int WD, int STRIDE, int G>
 __device__ __forceinline__ void gather_in(const double* __restrict__ g, double* rows, int off, int ng, int lane, long long myfid) {
-  for (int base = 0; base < ng * WD; base += 32) {
-    const int idx = base + lane;
+  constexpr int NIT = (G * WD + 31) / 32;
+  double v[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = it * 32 + lane;
     const bool ok = idx < ng * WD;
     const int f = ok ? idx / WD : 0, i = idx - f * WD;
     const long long fid = __shfl_sync(0xffffffffu, myfid, f);
-    if (ok) rows[f * STRIDE + off + i] = g[fid * WD + i];
+    v[it] = ok ? g[fid * WD + i] : 0.0;
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = it * 32 + lane;
+    const int f = idx / WD, i = idx - f * WD;
+    if (idx < ng * WD) rows[f * STRIDE + off + i] = v[it];
   }
 }
 template <int WD, int STRIDE>
@@ -173,8 +202,12 @@ __device__ __forceinline__ void scatter_out(double* __restrict__ g, const double
   }
 }
 
+#ifndef RNB_MIN_WARPS
+#define RNB_MIN_WARPS 12   // resident warps per SM the register allocator must allow (170 registers per thread)
+#endif
+
 template <class M, class K, bool PRED, bool UPD, int G, int W, bool GATHER>
-__global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a) {
+__global__ void __launch_bounds__(W * 32, RNB_MIN_WARPS / W) ekf_step_warp(const StepArgs<M::NG> a) {
   constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM;
   using L = RowLayout<M, K>;
   constexpr int RS = L::STRIDE;
@@ -247,14 +280,14 @@ __global__ void __launch_bounds__(W * 32) ekf_step_warp(const StepArgs<M::NG> a)
 
     // ---- stage this group's small per-filter records into the rows (coalesced) ----
     if (o == 0) {
-      if (gathered) gather_in<D, RS>(a.x, s.rows, L::OFF_X, ng, lane, myfid);
-      else stage_in<D, RS>(a.x + b0 * D, s.rows, L::OFF_X, ng, lane);
+      if (gathered) gather_in<D, RS, G>(a.x, s.rows, L::OFF_X, ng, lane, myfid);
+      else stage_in<D, RS, G>(a.x + b0 * D, s.rows, L::OFF_X, ng, lane);
     }
     if constexpr (UPD) {
       const bool shared_R = a.flags & FLAG_SHARED_R;
       if (a.n_obs == 1) {
-        stage_in<Z, RS>(a.z + b0 * Z, s.rows, L::OFF_Y, ng, lane);
-        if (!shared_R) stage_in<Z * Z, RS>(a.R + b0 * (Z * Z), s.rows, L::OFF_R, ng, lane);
+        stage_in<Z, RS, G>(a.z + b0 * Z, s.rows, L::OFF_Y, ng, lane);
+        if (!shared_R) stage_in<Z * Z, RS, G>(a.R + b0 * (Z * Z), s.rows, L::OFF_R, ng, lane);
       } else if (mine) {
         const long long bo = (b0 + lane) * a.n_obs + o;
 #pragma unroll

@@ -416,7 +416,7 @@ def test_batched_kalmanfilter_front_end(gen_dir, oracle_dir):
     obs_noise = KinematicKalman.obs_noise
 
     def __init__(self):
-      self.filter = _engine(gen_dir, "kinematic", Qm, x, P)
+      self.filter = _engine(gen_dir, "kinematic", x, P, Qm)
 
   kf = BatchedKinematic()
   kf.predict_and_observe(0.0, 1, z)
