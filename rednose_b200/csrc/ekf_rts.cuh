@@ -156,11 +156,13 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp(con
       const double di = 1.0 / s.LT[kk * LD + kk];
       if (lane == 0) s.dinv[kk] = di;
       const double cj = s.LT[kk * LD + (act ? lane : 0)] * di;   // D[kk] L[lane][kk] / D[kk] ... = L[lane][kk]
+      // rows i <= kk of A are final (already published) and never read again, so the update needs no
+      // predicate: it may clobber them freely
 #pragma unroll
       for (int i = 0; i < N; i += 2) {
         const double2 c2 = *reinterpret_cast<const double2*>(&s.LT[kk * LD + i]);
-        if (i > kk) A[i] = fma(-c2.x, cj, A[i]);
-        if (i + 1 > kk && i + 1 < N) A[i + 1] = fma(-c2.y, cj, A[i + 1]);
+        A[i] = fma(-c2.x, cj, A[i]);
+        if (i + 1 < N) A[i + 1] = fma(-c2.y, cj, A[i + 1]);
       }
     }
     __syncwarp();
@@ -175,7 +177,10 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp(con
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] *= s.dinv[i];
 #pragma unroll
-    const volatile double* LTv = s.LT;  // re-read L: without this ptxas keeps all of L from the forward sweep (spills)
+    // re-read L through a laundered pointer: otherwise ptxas keeps every row of L loaded by the forward sweep
+    // alive in registers for the backward sweep (1.4 kB of spills); laundering keeps the 128-bit loads
+    const double* LTv = s.LT;
+    asm volatile("" : "+l"(LTv));
 #pragma unroll
     for (int kk = N - 2; kk >= 0; --kk) {
       double acc = 0.0;
