@@ -37,6 +37,21 @@ static inline void matmul(const double* __restrict__ A, const double* __restrict
   }
 }
 
+// same loop with compile-time extents (what Eigen's fixed-size matrices give the reference, ekf_c.c:4-6,20-26):
+// the compiler can unroll / vectorise; summation order per element is unchanged
+template <int M_, int K_, int N_>
+static inline void matmul_fixed(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C) {
+  for (int i = 0; i < M_; ++i) {
+    double* c = C + (size_t)i * N_;
+    for (int j = 0; j < N_; ++j) c[j] = 0.0;
+    for (int l = 0; l < K_; ++l) {
+      const double a = A[i * K_ + l];
+      const double* b = B + (size_t)l * N_;
+      for (int j = 0; j < N_; ++j) c[j] += a * b[j];
+    }
+  }
+}
+
 static inline void transpose(const double* A, double* At, int m, int n) {
   for (int i = 0; i < m; ++i)
     for (int j = 0; j < n; ++j) At[j * m + i] = A[i * n + j];
@@ -148,8 +163,8 @@ void predict(double* in_x, double* in_P, double* in_Q, double dt) {
   std::vector<double> Pmm((size_t)M * M), T((size_t)M * M), T2((size_t)M * M);
   for (int i = 0; i < M; ++i)
     for (int j = 0; j < M; ++j) Pmm[i * M + j] = P[i * EDIM + j];
-  matmul(Fm.data(), Pmm.data(), T.data(), M, M, M);
-  matmul(T.data(), FmT.data(), T2.data(), M, M, M);
+  matmul_fixed<MEDIM, MEDIM, MEDIM>(Fm.data(), Pmm.data(), T.data());
+  matmul_fixed<MEDIM, MEDIM, MEDIM>(T.data(), FmT.data(), T2.data());
   if (A > 0) {
     // P_ma <- F_mm P_ma ; P_am <- P_am F_mm^T    ekf_c.c:25-26
     std::vector<double> Pma((size_t)M * A), Pam((size_t)A * M), Ra((size_t)M * A), Rb((size_t)A * M);
@@ -268,9 +283,9 @@ void update(double* in_x, double* in_P, Hfun h_fun, Hfun H_fun, Hfun Hea_fun, do
 
   // P <- (I_KH P) I_KH^T + (K R) K^T      ekf_c.c:115
   std::vector<double> T((size_t)EDIM * EDIM), Pn((size_t)EDIM * EDIM), KR((size_t)EDIM * m), KRKt((size_t)EDIM * EDIM);
-  matmul(I_KH.data(), P.data(), T.data(), EDIM, EDIM, EDIM);
+  matmul_fixed<EDIM, EDIM, EDIM>(I_KH.data(), P.data(), T.data());
   transpose(I_KH.data(), I_KHt.data(), EDIM, EDIM);
-  matmul(T.data(), I_KHt.data(), Pn.data(), EDIM, EDIM, EDIM);
+  matmul_fixed<EDIM, EDIM, EDIM>(T.data(), I_KHt.data(), Pn.data());
   matmul(K.data(), R.data(), KR.data(), EDIM, m, m);
   matmul(KR.data(), KT.data(), KRKt.data(), EDIM, m, EDIM);
   for (int i = 0; i < EDIM * EDIM; ++i) Pn[i] += KRKt[i];

@@ -22,15 +22,16 @@ def normalise(expr):
   Filter definitions are built from numpy arrays (examples/live_kf.py:161,180,187),
   so matrices are full of ``Float(0.0)`` which sympy >= 1.13 no longer equates with 0.
   """
-  reps = {f: sp.Integer(int(f)) for f in expr.atoms(sp.Float) if f == int(f)}
+  # compare as Python floats: Float(0.0) == 0 is False in sympy >= 1.13
+  reps = {f: sp.Integer(int(f)) for f in expr.atoms(sp.Float) if abs(float(f)) <= 16.0 and float(f) == int(float(f))}  # small structural constants only
   return expr.xreplace(reps) if reps else expr
 
 
 def is_structural_zero(e, expand_limit=400):
-  if e == 0:
+  if e == 0 or e.is_zero:
     return True
   if e.is_number:
-    return bool(e == 0)
+    return float(e) == 0.0
   if sp.count_ops(e) <= expand_limit:
     return sp.expand(e) == 0
   return False
