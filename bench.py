@@ -158,6 +158,11 @@ def run_gpu(args):
     from rednose_b200.filters.kinematic import KinematicKalman as FilterCls
   else:
     from rednose_b200.filters.live import LiveKalman as FilterCls
+  # only one rank per node may (re)build the filter library; the others wait
+  if local_rank == 0:
+    lib_dir = ensure_generated(FilterCls)
+  if world > 1:
+    dist.barrier()
   lib_dir = ensure_generated(FilterCls)
 
   x0, P0, Q, pools, (dim, edim), quat = make_problem(fname, B, seed=1234 + rank, lib_dir=lib_dir)
@@ -462,8 +467,9 @@ def run_extras(dev, peak):
     zp = torch.as_tensor(hz[None, :] + rng.normal(0, 1e-3, (B, 20))).to(dev)
     Rk = torch.as_tensor(np.eye(20) * 1e-6).to(dev)
     ea = torch.as_tensor(np.tile(point, (B, 1))).to(dev)
-    def mstep():
+    def mstep():   # one camera frame: fused predict + gated feature update, then the clone window shifts (augment=True)
       e.step(17, 0.01, zp.clone(), Rk, ea=ea)
+      e.augment()
     ms = _time_ms(mstep, 10, torch, dev)
     bs = 8 * (2 * EDIM * EDIM + 2 * DIM + 20 + 400 + 17 + 3 + 1)
     out["msckf_10k_feature_step"] = {"filters": B, "ms_per_step": ms, "steps_per_s": B / (ms * 1e-3), "GBps_algorithmic": bs * B / (ms * 1e-3) / 1e9,
@@ -501,7 +507,27 @@ def cpu_reference(fname, workload, budget_s=15.0, steps=None):
     x, P, _ = o.batch_step(k, x, P, Q, 0.01, zp[i % zp.shape[0]], R, quat_idxs=quat, flags=3, nthreads=cores)
   el = time.perf_counter() - t
   assert np.isfinite(x).all()
+  # context numbers: one thread, and the per-filter Python driving pattern the reference ships
+  n1 = min(Bs, 4000)
+  t1 = time.perf_counter()
+  o.batch_step(sched[1], x[:n1], P[:n1], Q, 0.01, pools[sched[1]][0][0][:n1], pools[sched[1]][1][:n1], quat_idxs=quat, flags=3, nthreads=1)
+  one_thread = n1 / (time.perf_counter() - t1)
+  py_driver = None
+  try:
+    from rednose_b200.ekf_sym import EKF_sym
+    kf = EKF_sym(build_ref.OUT, fname, Q, x[0], P[0], dim, edim, quaternion_idxs=quat)   # Python driver on the CPU oracle library
+    k = sched[1]
+    zp, R = pools[k]
+    tt, n_calls = 0.0, 300
+    t2 = time.perf_counter()
+    for i in range(n_calls):
+      tt += 0.01
+      kf.predict_and_update_batch(tt, k, zp[0][i:i + 1], R[i:i + 1])
+    py_driver = n_calls / (time.perf_counter() - t2)
+  except Exception:  # pylint: disable=broad-except
+    pass
   return {"value": Bs * n_steps / el, "unit": "steps/s", "cores": cores, "kind": "port",
+          "one_thread_steps_per_s": one_thread, "python_driver_per_filter_steps_per_s": py_driver,
           "sample": f"{Bs} {fname} filters x {n_steps} steps of workload {workload} (same kind schedule), {el:.1f} s",
           "what": "reference-generated leaf C (rednose gen_code, unmodified) + Eigen-free restatement of ekf_c.c, g++ -O2, threads over filters"}
 

@@ -45,15 +45,26 @@ def compile_filter(folder, name, force=False, verbose=False):
   lib = os.path.join(folder, f"lib{name}.so")
   if not force and _newer(lib, [src] + csrc_sources()):
     return lib
+  import fcntl
+  with open(os.path.join(folder, f".{name}.lock"), "w") as lock:   # concurrent builders (one process per GPU) serialise here
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    if not force and _newer(lib, [src] + csrc_sources()):
+      return lib
+    return _compile_filter_locked(folder, name, src, lib, verbose)
+
+
+def _compile_filter_locked(folder, name, src, lib, verbose):
   tune = [f"-D{k}={os.environ[e]}" for k, e in (("RNB_GROUP", "REDNOSE_B200_GROUP"), ("RNB_WARPS", "REDNOSE_B200_WARPS"), ("RNB_TMA", "REDNOSE_B200_TMA"), ("RNB_STAGES", "REDNOSE_B200_STAGES"), ("RNB_TMA_STORE", "REDNOSE_B200_TMA_STORE"), ("RNB_SMALLSYM", "REDNOSE_B200_SMALLSYM"), ("RNB_STAGE_BATCHED", "REDNOSE_B200_STAGE_BATCHED")) if os.environ.get(e)]
   if os.environ.get("REDNOSE_B200_MAXRREG"):
     tune += ["-maxrregcount", os.environ["REDNOSE_B200_MAXRREG"]]
-  cmd = [nvcc_path()] + NVCC_FLAGS + tune + ["-Xptxas", "-v", f"-I{CSRC_DIR}", f"-I{INCLUDE_DIR}", "-o", lib, src]
+  tmp = lib + f".tmp{os.getpid()}"
+  cmd = [nvcc_path()] + NVCC_FLAGS + tune + ["-Xptxas", "-v", f"-I{CSRC_DIR}", f"-I{INCLUDE_DIR}", "-o", tmp, src]
   res = subprocess.run(cmd, capture_output=True, text=True)
   with open(os.path.join(folder, f"{name}.ptxas.log"), "w", encoding="utf-8") as f:
     f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
   if res.returncode != 0:
     raise RuntimeError(f"nvcc failed for {src}:\n{res.stderr[-4000:]}")
+  os.replace(tmp, lib)   # atomic: a reader never sees a half-written library
   if verbose:
     print(res.stderr)
   return lib
