@@ -2,7 +2,8 @@
 """Time (and optionally profile) the batched RTS backward kernel on a recorded live history."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+
+import torch
 from bench import make_problem, kind_schedule
 from rednose_b200.batched import BatchedEKF
 from rednose_b200.filters import ensure_generated

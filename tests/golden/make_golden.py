@@ -31,7 +31,6 @@ def main():
   from rednose.helpers.ekf_sym import EKF_sym
   import rednose
   assert os.path.realpath(rednose.__file__).startswith(REF), rednose.__file__
-  from rednose_b200.filters.live import LiveKalman
   from tests.util import LIVE_KINDS, LIVE_R, live_batch
 
   rng = np.random.default_rng(2024)

@@ -2,7 +2,6 @@
 updates with left-null-space projection and Mahalanobis gating, state augmentation."""
 import numpy as np
 import pytest
-import torch
 
 from tests.util import Oracle, live_obs, msckf_batch, msckf_feature_obs, rel_err
 

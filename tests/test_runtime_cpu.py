@@ -1,6 +1,4 @@
 """CPU tests of librednose_b200.so: plugin registry (rednose/helpers/ekf_load.cc) and native driver plumbing."""
-import ctypes
-
 import numpy as np
 
 from rednose_b200.ekf_sym_pyx import EKF_sym_pyx, runtime

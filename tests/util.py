@@ -1,5 +1,4 @@
 """Shared helpers for the parity tests: oracle access (test infrastructure) and synthetic inputs."""
-import os
 
 import numpy as np
 
