@@ -49,7 +49,7 @@ struct RtsArgs {
 
 constexpr int RTS_WARPS = 2;
 #ifndef RNB_RTS_MIN_CTAS
-#define RNB_RTS_MIN_CTAS 6
+#define RNB_RTS_MIN_CTAS 8
 #endif
 constexpr int RTS_MIN_CTAS = RNB_RTS_MIN_CTAS;
 
@@ -59,7 +59,7 @@ struct RtsScratch {
   static constexpr int LD = (N + 3) & ~1;             // even leading dimension (128-bit rows), not a multiple of 32 banks
   alignas(16) double LT[N * LD];                      // LT[k][i] = unscaled column k of the trailing matrix = D[k] L[i][k] (i >= k)
   alignas(16) double DP[N * LD];                      // dP = P_{k+1|N} - P_{k+1|k}; later X (row-major)
-  alignas(16) double YS[N * 32];                      // y = dP X, column per lane
+  // y = dP X (column per lane) lives in the LT buffer: L is dead once the substitutions are done
   alignas(16) double xf[(M::DIM + 1) & ~1];           // x_{k|k}
   alignas(16) double xp[(M::DIM + 1) & ~1];           // x_{k+1|k}
   alignas(16) double xn[(M::DIM + 1) & ~1];           // x_{k+1|N} -> x_{k|N}
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp(con
         acc = fma(d2.x, g[c], acc);
         if (c + 1 < N) acc = fma(d2.y, g[c + 1], acc);
       }
-      s.YS[i * 32 + lane] = acc;
+      if (act) s.LT[i * LD + lane] = acc;
     }
     __syncwarp();
     if (act) {  // X row-major into the dP buffer: XS[r][lane] = X[r][lane]
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp(con
     for (int i = 0; i < N; ++i) pn[i] = Pf_g[i * E];
 #pragma unroll 1
     for (int r = 0; r < N; ++r) {
-      const double yr = s.YS[r * 32 + lane];
+      const double yr = s.LT[r * LD + (act ? lane : 0)];
 #pragma unroll
       for (int i = 0; i < N; i += 2) {
         const double2 x2 = *reinterpret_cast<const double2*>(&s.DP[r * LD + i]);
