@@ -2,6 +2,7 @@
 updates with left-null-space projection and Mahalanobis gating, state augmentation."""
 import numpy as np
 import pytest
+import torch
 
 from tests.util import Oracle, live_obs, msckf_batch, msckf_feature_obs, rel_err
 
@@ -100,3 +101,29 @@ def test_batched_augment_equals_reference_selection(msckf_dirs):
   to_mult[-d4:, :d4] = np.eye(d4)
   Pr = np.stack([to_mult @ np.delete(np.delete(Pb, np.s_[d2:d2 + d4], axis=1), np.s_[d2:d2 + d4], axis=0) @ to_mult.T for Pb in P])
   assert np.array_equal(e.state(), xr) and np.array_equal(e.covs(), Pr)
+
+
+def test_msckf_two_observations_per_predict_and_gather_list(msckf_dirs):
+  """CTA path: n_obs = 2 (leaf + CTA kernels re-launched per observation) and the gather-list variant."""
+  gen_dir, oracle_dir = msckf_dirs
+  o, ol = Oracle(oracle_dir, "msckf"), Oracle(oracle_dir, "live")
+  B = 21
+  x, P, Q, _ = msckf_batch(B, seed=11)
+  z1, R1 = live_obs(ol, 12, x[:, :23], seed=1)
+  z2, R2 = live_obs(ol, 12, x[:, :23], seed=2)
+  xr, Pr = o.predict(x, P, Q, 0.02)
+  xr, Pr, _ = o.update(12, xr, Pr, z1, R1)
+  xr, Pr, _ = o.update(12, xr, Pr, z2, R2)
+  e = _engine(gen_dir, x, P, Q, norm_after_predict=False, norm_after_update=False)
+  e.step(12, 0.02, np.stack([z1, z2], 1), np.stack([R1, R2], 1))
+  assert rel_err(e.state(), xr) < 1e-9 and rel_err(e.covs(), Pr) < 1e-8
+  # gather list: only the odd filters step; the even ones must stay bit-identical
+  e2 = _engine(gen_dir, x, P, Q)
+  idx = torch.arange(1, B, 2, dtype=torch.int32, device="cuda")
+  sel = idx.cpu().numpy()
+  e2.step_indexed(12, idx, 0.02, z1[sel], R1[sel])
+  xs, Ps, _ = o.batch_step(12, x[sel], P[sel], Q, 0.02, z1[sel], R1[sel], quat_idxs=QUATS, flags=3)
+  got_x, got_P = e2.state(), e2.covs()
+  assert rel_err(got_x[sel], xs) < 1e-9 and rel_err(got_P[sel], Ps) < 1e-8
+  keep = np.setdiff1d(np.arange(B), sel)
+  assert np.array_equal(got_x[keep], x[keep]) and np.array_equal(got_P[keep], P[keep])

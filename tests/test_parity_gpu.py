@@ -425,3 +425,37 @@ def test_batched_kalmanfilter_front_end(gen_dir, oracle_dir):
   xr, Pr, _ = o.batch_step(1, xr, Pr, Qm, 0.05, z, R)
   assert rel_err(kf.x, xr) < TIGHT and rel_err(kf.P, Pr) < TIGHT and kf.t == 0.05
   assert kf.maha_test(1, z).shape == (B,)
+
+
+def test_gather_list_on_the_thread_kernel(gen_dir, oracle_dir):
+  o = Oracle(oracle_dir, "kinematic")
+  B = 1001
+  x, P, Qm, z, R = kinematic_batch(B, seed=77)
+  e = _engine(gen_dir, "kinematic", x, P, Qm)
+  idx = torch.as_tensor(np.random.default_rng(0).permutation(B)[:400].astype(np.int32)).cuda()   # unordered subset
+  sel = idx.cpu().numpy()
+  dt = torch.linspace(0.001, 0.02, 400, dtype=torch.float64)
+  e.step_indexed(1, idx, dt, z[sel], R[sel])
+  xr, Pr, _ = o.batch_step(1, x[sel], P[sel], Qm, dt.numpy(), z[sel], R[sel])
+  gx, gP = e.state(), e.covs()
+  assert rel_err(gx[sel], xr) < TIGHT and rel_err(gP[sel], Pr) < TIGHT
+  keep = np.setdiff1d(np.arange(B), sel)
+  assert np.array_equal(gx[keep], x[keep]) and np.array_equal(gP[keep], P[keep])
+
+
+def test_live_long_stream_2000_steps(gen_dir, oracle_dir):
+  """Drift check: 2000 fused steps (20 s of 100 Hz IMU + 1 Hz fixes) stay within the contract of the oracle."""
+  o = Oracle(oracle_dir, "live")
+  B = 16
+  x, P, Qm = live_batch(B, seed=2000, well_conditioned=False)
+  e = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  xr, Pr = x.copy(), P.copy()
+  worst = 0.0
+  for k in range(2000):
+    kind = 12 if k % 100 == 0 else (4 if k % 2 else 10)
+    z, R = live_obs(o, kind, xr, seed=5000 + k)
+    xr, Pr, _ = o.batch_step(kind, xr, Pr, Qm, 0.01, z, R, quat_idxs=[3], flags=3, nthreads=1)
+    e.step(kind, 0.01, z, R)
+    if k % 250 == 249:
+      worst = max(worst, rel_err(e.state(), xr), rel_err(e.covs(), Pr))
+  assert worst < 1e-7, worst
