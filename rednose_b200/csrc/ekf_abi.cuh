@@ -11,6 +11,7 @@
 #include "ekf_warp.cuh"
 #include "ekf_cta.cuh"
 #include "ekf_rts.cuh"
+#include "ekf_rts_mma.cuh"
 #include "ekf_augment.cuh"
 #include <cstring>
 #include <mutex>
@@ -168,7 +169,7 @@ inline void batch_rts(HostCtx<M>& ctx, const double* hx_pred, const double* hP_p
   a.n_quat = n_quat < 0 ? 0 : (n_quat > MAX_QUAT ? MAX_QUAT : n_quat);
   for (int i = 0; i < a.n_quat; ++i) a.quat_idx[i] = quat_idxs[i];
   for (int i = 0; i < (M::NG > 0 ? M::NG : 1); ++i) a.gv[i] = ctx.gv.v[i];
-  launch_rts<M>(a, (cudaStream_t)stream);
+  launch_rts_auto<M>(a, (cudaStream_t)stream);
 }
 
 // --------------------------------------------- batched, HOST buffers (stateless) ---
