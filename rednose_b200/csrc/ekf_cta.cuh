@@ -20,6 +20,7 @@
 #pragma once
 #include "ekf_common.cuh"
 #include "ekf_warp.cuh"
+#include "ekf_rts_mma.cuh"   // dmma884
 
 namespace rnb {
 
@@ -130,10 +131,11 @@ template <class M, class K>
 struct CtaSmem {
   static constexpr int E = M::EDIM, Z = K::ZDIM, Y = K::YDIM;
   static constexpr int LD = E | 1;                 // odd: row and column sweeps are both conflict-free
-  static constexpr int HL = (Z + 1) & ~1;          // leading dimension of the HP buffer ([column][c])
+  static constexpr int HL = (Z + 3) & ~3;          // leading dimension of the HP / W buffers ([column][c]); multiple of the mma k = 4
   static constexpr int SL = Z | 1;
   double P[E * LD];
   double HP[E * HL];                               // (H_err P)[c][k] stored as HP[k * HL + c]
+  double W[E * HL];                                // S^-1 (H_err P), same layout (B operand of the rank-m update)
   double S[Z * SL];                                // H_err P H_err^T (projected in place)
   double Rm[Z * SL];                               // R (projected in place)
   double LT[Z * SL];                               // LDL^T factor of S, transposed
@@ -174,7 +176,7 @@ constexpr int cta_tpg() { return ((M::EDIM + 31) / 32) * 32; }   // threads per 
 constexpr int CTA_GROUPS = 2;                                      // groups split the rows of the rank-m covariance update
 
 template <class M, class K, bool PRED, bool UPD>
-__global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS) ekf_step_cta(const StepArgs<M::NG> a, int o, const double* __restrict__ ws_all) {
+__global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS, 2) ekf_step_cta(const StepArgs<M::NG> a, int o, const double* __restrict__ ws_all) {
   constexpr int D = M::DIM, E = M::EDIM, ME = M::MEDIM, Z = K::ZDIM, Y = K::YDIM, NR = Z - Y;
   using SM = CtaSmem<M, K>;
   using W = CtaWs<M, K>;
@@ -308,7 +310,6 @@ __global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS) ekf_step_cta(const 
     if (own0) {
 #pragma unroll
       for (int c = 0; c < Y; ++c) s.HP[col * HL + c] = hp[NR + c];
-      if (Y < HL) s.HP[col * HL + Y] = 0.0;
     }
 
     // ---- factor S = S_raw + R (warp 0, lane j = column j), gate, refactor if gated ----
@@ -383,38 +384,31 @@ __global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS) ekf_step_cta(const 
         s.dx[col] = dxl;
       }
     }
-    __syncthreads();  // HP (projected) complete in shared memory
-    if (own) {
-      // P[:, col] -= HP^T w; the groups split the rows
-      constexpr int RPG = (E + CTA_GROUPS - 1) / CTA_GROUPS;
-      const int i0 = grp * RPG, i1 = (i0 + RPG < E) ? i0 + RPG : E;
-      // four rows at a time: four independent accumulation chains hide the FP64 latency
-      int i = i0;
-      for (; i + 4 <= i1; i += 4) {
-        double acc[4];
+    // ---- P -= HP^T W on the FP64 tensor path: 8 x 8 output tiles, k = Y padded to a multiple of 4 ----
+    if (own0) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r] = s.P[(i + r) * LD + col];
+      for (int c = 0; c < HL; ++c) s.W[col * HL + c] = (c < Y) ? w[c < Y ? c : 0] : 0.0;
 #pragma unroll
-        for (int c = 0; c < Y; c += 2) {
+      for (int c = Y; c < HL; ++c) s.HP[col * HL + c] = 0.0;
+    }
+    __syncthreads();  // HP (projected) and W complete in shared memory
+    {
+      constexpr int NTE = (E + 7) / 8, NKY = HL / 4;
+      const int lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+      const int fg = lane >> 2, ft = lane & 3;
+      for (int tile = warp; tile < NTE * NTE; tile += nwarps) {
+        const int mi = tile / NTE, ni = tile - mi * NTE;
+        const int r = mi * 8 + fg, c = ni * 8 + 2 * ft, n = ni * 8 + fg;
+        double c0 = (r < E && c < E) ? s.P[r * LD + c] : 0.0;
+        double c1 = (r < E && c + 1 < E) ? s.P[r * LD + c + 1] : 0.0;
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const double2 h2 = *reinterpret_cast<const double2*>(&s.HP[(i + r) * HL + c]);
-            acc[r] = fma(-h2.x, w[c], acc[r]);
-            if (c + 1 < Y) acc[r] = fma(-h2.y, w[c + 1], acc[r]);
-          }
+        for (int kq = 0; kq < NKY; ++kq) {
+          const double av = (r < E) ? -s.HP[r * HL + kq * 4 + ft] : 0.0;   // A[m][k] = -(HP)^T
+          const double bv = (n < E) ? s.W[n * HL + kq * 4 + ft] : 0.0;     // B[k][n] = W
+          dmma884(c0, c1, av, bv);
         }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) s.P[(i + r) * LD + col] = acc[r];
-      }
-      for (; i < i1; ++i) {
-        double acc = s.P[i * LD + col];
-#pragma unroll
-        for (int c = 0; c < Y; c += 2) {
-          const double2 h2 = *reinterpret_cast<const double2*>(&s.HP[i * HL + c]);
-          acc = fma(-h2.x, w[c], acc);
-          if (c + 1 < Y) acc = fma(-h2.y, w[c + 1], acc);
-        }
-        s.P[i * LD + col] = acc;
+        if (r < E && c < E) s.P[r * LD + c] = c0;
+        if (r < E && c + 1 < E) s.P[r * LD + c + 1] = c1;
       }
     }
     // state injection (every thread evaluates the small generated function; identical values)
