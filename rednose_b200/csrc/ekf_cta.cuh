@@ -194,9 +194,21 @@ __global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS, 2) ekf_step_cta(con
   const bool own0 = own && grp == 0;   // ... and is the one that writes per-column results
 
   // ---- stage: covariance tile (coalesced, re-pitched), leaf values ----
-  for (int idx = tid; idx < E * E; idx += nth) {
-    const int i = idx / E, j = idx - i * E;
-    s.P[i * LD + j] = Pg[idx];
+  {
+    // all loads of the tile are issued before the first shared-memory store (one global round trip, not one per pass)
+    constexpr int NIT = (E * E + TPG * CTA_GROUPS - 1) / (TPG * CTA_GROUPS);
+    double v[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = it * nth + tid;
+      v[it] = (idx < E * E) ? Pg[idx] : 0.0;
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = it * nth + tid;
+      const int i = idx / E, j = idx - i * E;
+      if (idx < E * E) s.P[i * LD + j] = v[it];
+    }
   }
   for (int i = tid; i < D; i += nth) s.x[i] = ws[W::OFF_X + i];
   if constexpr (PRED) {
