@@ -49,7 +49,7 @@ struct RtsArgs {
 
 constexpr int RTS_WARPS = 2;
 #ifndef RNB_RTS_MIN_CTAS
-#define RNB_RTS_MIN_CTAS 8
+#define RNB_RTS_MIN_CTAS 6
 #endif
 constexpr int RTS_MIN_CTAS = RNB_RTS_MIN_CTAS;
 

@@ -94,22 +94,10 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp_mma
     const double* Pp_b = a.hP_pred + (k + 1) * BP + b * (long long)(E * E);
     const double* Pf_g = Pf_b + col;
     const double* Pp_g = Pp_b + col;
-    double g[N];
+    // every global load of the step is issued here, before any dependent work (one latency round trip per step)
+    double g[N], A[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) g[i] = Pf_g[i * E];
-    for (int i = lane; i < D; i += 32) {
-      s.xf[i] = a.hx_filt[k * BX + b * D + i];
-      s.xp[i] = a.hx_pred[(k + 1) * BX + b * D + i];
-    }
-    const double dt = a.t_per_filter ? (a.t[(k + 1) * a.B + b] - a.t[k * a.B + b]) : (a.t[k + 1] - a.t[k]);
-    __syncwarp();
-    {
-      double fv[M::NF > 0 ? M::NF : 1];
-      M::F_vals(s.xf, dt, a.gv, fv);
-      M::F_apply(fv, g);   // G[:,lane] = F P_{k|k}[:,lane]
-    }
-    asm volatile("" ::: "memory");
-
+    for (int i = 0; i < N; ++i) { g[i] = Pf_g[i * E]; A[i] = Pp_g[i * E]; }
     // dP = P_{k+1|N} - P_{k+1|k} in fragment layout -> shared memory (zero padded)
 #pragma unroll
     for (int mi = 0; mi < NT; ++mi)
@@ -125,10 +113,19 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp_mma
         *reinterpret_cast<double2*>(&s.DP[r * LP + c]) = v;
       }
 
+    for (int i = lane; i < D; i += 32) {
+      s.xf[i] = a.hx_filt[k * BX + b * D + i];
+      s.xp[i] = a.hx_pred[(k + 1) * BX + b * D + i];
+    }
+    const double dt = a.t_per_filter ? (a.t[(k + 1) * a.B + b] - a.t[k * a.B + b]) : (a.t[k + 1] - a.t[k]);
+    __syncwarp();
+    {
+      double fv[M::NF > 0 ? M::NF : 1];
+      M::F_vals(s.xf, dt, a.gv, fv);
+      M::F_apply(fv, g);   // G[:,lane] = F P_{k|k}[:,lane]
+    }
+
     // ---- P_{k+1|k} = L D L^T (rolled right-looking factorisation, as in ekf_rts_warp) ----
-    double A[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) A[i] = Pp_g[i * E];
 #pragma unroll 1
     for (int kk = 0; kk < N; ++kk) {
       if (lane == kk) {
