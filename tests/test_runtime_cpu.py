@@ -60,3 +60,61 @@ def test_product_fails_loudly_without_a_gpu(gen_dir):
     kf.predict_and_update_batch(0.0, 1, np.array([[0.1]]), np.array([[[0.01]]]))
   with pytest.raises(RuntimeError, match="no CPU fallback"):
     BatchedEKF(gen_dir, "kinematic", np.diag([0.01, 4.0]), np.array([0.5, 0.0]), np.eye(2), batch=4)
+
+
+def test_augment_native_driver_equals_python_driver_and_reference_formula(oracle_dir):
+  """MSCKF clone-window shift (ekf_sym.py:365-391): the C++ driver, the Python driver and the selection-matrix
+  formula of the reference agree bit for bit; augment=True inside predict_and_update_batch shifts after the update."""
+  import os
+  import pytest
+  from oracle import build_ref
+  if build_ref.reference_available():
+    build_ref.build("msckf", "rednose_b200.filters.msckf:MsckfKalman")
+  if not os.path.exists(os.path.join(oracle_dir, "libmsckf.so")):
+    pytest.skip("oracle/_ref/libmsckf.so not built")
+  from rednose_b200.ekf_sym import EKF_sym
+  from rednose_b200.filters.msckf import MsckfKalman as F
+  from tests.util import msckf_batch
+  x, P, Q, _ = msckf_batch(1, seed=4)
+  kw = dict(N=10, dim_augment=7, dim_augment_err=6, quaternion_idxs=[3])
+  a = EKF_sym_pyx(oracle_dir, "msckf", Q, x[0], P[0], 23, 22, **kw)
+  b = EKF_sym(oracle_dir, "msckf", Q, x[0], P[0], 23, 22, **kw)
+  a.set_filter_time(1.5); b.set_filter_time(1.5)
+  a.augment(); b.augment()
+  d1, d2, d3, d4, n = 23, 22, 7, 6, 82
+  xr = x[0].copy()
+  xr[d1:-d3] = x[0][d1 + d3:]
+  xr[-d3:] = x[0][:d3]
+  T = np.zeros((n, n - d4))
+  T[:-d4, :] = np.eye(n - d4)
+  T[-d4:, :d4] = np.eye(d4)
+  Pr = T @ np.delete(np.delete(P[0], np.s_[d2:d2 + d4], axis=1), np.s_[d2:d2 + d4], axis=0) @ T.T
+  for kf in (a, b):
+    assert np.array_equal(kf.state(), xr) and np.array_equal(kf.covs(), Pr)
+    assert kf.get_augment_times()[-1] == 1.5 and len(kf.get_augment_times()) == 10
+  # augment=True through the batch call: update first, then shift (ekf_sym.py:525-526)
+  z, R = x[0][None, :3] + 0.1, np.diag([25.0] * 3)[None]
+  ra = a.predict_and_update_batch(1.6, 12, z, R, augment=True)
+  rb = b.predict_and_update_batch(1.6, 12, z, R, augment=True)
+  assert np.allclose(ra[1], rb[1], rtol=0, atol=1e-9) and np.allclose(a.state(), b.state(), rtol=0, atol=1e-9)
+  assert np.allclose(a.state()[-7:], a.state()[:7]) and np.allclose(a.covs(), b.covs(), rtol=1e-12, atol=1e-12)
+
+
+def test_python_maha_test_follows_the_reference_formula(oracle_dir):
+  """EKF_sym.maha_test (ekf_sym.py:626-649) on the CPU oracle library."""
+  from rednose_b200.chi2 import chi2_ppf
+  from rednose_b200.ekf_sym import EKF_sym
+  from rednose_b200.filters.live import LiveKalman as F
+  from tests.util import Oracle, live_batch, live_obs
+  o = Oracle(oracle_dir, "live")
+  x, P, Q = live_batch(6, seed=8)
+  kf = EKF_sym(oracle_dir, "live", Q, x[0], P[0], 23, 22)
+  z, R = live_obs(o, 4, x, seed=3, noise_scale=4.0)
+  for b in range(6):
+    h, H, Hm = np.zeros(3), np.zeros(3 * 23), np.zeros(23 * 22)
+    xb = np.ascontiguousarray(x[b])
+    o.leaf("h_4", xb, np.zeros(1), h); o.leaf("H_4", xb, np.zeros(1), H); o.leaf("H_mod_fun", xb, Hm)
+    He = H.reshape(3, 23) @ Hm.reshape(23, 22)
+    y = z[b] - h
+    d = y @ np.linalg.inv(He @ P[b] @ He.T + R[b]) @ y
+    assert kf.maha_test(xb, P[b], 4, z[b], R[b]) == bool(d <= chi2_ppf(0.95, 3))
