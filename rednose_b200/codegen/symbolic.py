@@ -27,11 +27,33 @@ def normalise(expr):
   return expr.xreplace(reps) if reps else expr
 
 
+def _probe_value(e):
+  """Numeric value of e at a fixed pseudo-random point (None if it cannot be evaluated)."""
+  from sympy.matrices.expressions.matexpr import MatrixElement
+  reps = {}
+  for a in e.atoms(MatrixElement) | e.atoms(sp.Symbol):
+    if isinstance(a, sp.Symbol) and any(a in m.free_symbols for m in e.atoms(MatrixElement)):
+      continue  # the MatrixSymbol itself shows up as a free symbol of its elements
+    h = (hash(str(a)) % 9973) / 9973.0
+    reps[a] = sp.Float(0.37 + 0.91 * h)          # away from 0, 1 and the singular points of the usual models
+  try:
+    v = complex(sp.N(e.xreplace(reps), 20))
+  except (TypeError, ValueError):
+    return None
+  return abs(v)
+
+
 def is_structural_zero(e, expand_limit=400):
+  """True if e is identically zero.  Exact zeros are caught directly; anything else is first probed numerically
+  (a non-zero value at a generic point proves e != 0 and skips the expensive expand), and only expressions
+  that evaluate to ~0 are expanded symbolically to confirm the cancellation."""
   if e == 0 or e.is_zero:
     return True
   if e.is_number:
     return float(e) == 0.0
+  v = _probe_value(e)
+  if v is not None and v > 1e-9:
+    return False
   if sp.count_ops(e) <= expand_limit:
     return sp.expand(e) == 0
   return False
