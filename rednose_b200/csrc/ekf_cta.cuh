@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS, 2) ekf_step_cta(con
   using SM = CtaSmem<M, K>;
   using W = CtaWs<M, K>;
   constexpr int LD = SM::LD, HL = SM::HL, SL = SM::SL;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   SM& s = *reinterpret_cast<SM*>(smem_raw);
   constexpr int TPG = cta_tpg<M>();
   const int tid = threadIdx.x, nth = blockDim.x;

@@ -176,7 +176,6 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp(con
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] *= s.dinv[i];
-#pragma unroll
     // re-read L through a laundered pointer: otherwise ptxas keeps every row of L loaded by the forward sweep
     // alive in registers for the backward sweep (1.4 kB of spills); laundering keeps the 128-bit loads
     const double* LTv = s.LT;

@@ -459,3 +459,25 @@ def test_live_long_stream_2000_steps(gen_dir, oracle_dir):
     if k % 250 == 249:
       worst = max(worst, rel_err(e.state(), xr), rel_err(e.covs(), Pr))
   assert worst < 1e-7, worst
+
+
+def test_rts_scalar_fallback_on_the_kinematic_model(gen_dir, oracle_dir):
+  """Filters with MEDIM < 8 smooth through the scalar RTS kernel (ekf_rts_warp), not the DMMA variant."""
+  from oracle.rts_numpy import rts_smooth
+  o = Oracle(oracle_dir, "kinematic")
+  B, T = 40, 25
+  x, P, Qm, _, _ = kinematic_batch(B, seed=88)
+  e = _engine(gen_dir, "kinematic", x, P, Qm)
+  hist = e.new_history(T)
+  rng = np.random.default_rng(1)
+  for k in range(T):
+    z = e.state()[:, :1] + rng.normal(0, 0.1, (B, 1))
+    e.step_recorded(hist, 1, 0.01 * (k + 1), z, np.array([[0.01]]))
+  xs, Ps = e.rts_smooth(hist, norm_quats=False)
+  xs, Ps = xs.cpu().numpy(), Ps.cpu().numpy()
+  hx_p, hx_f = hist.x_pred.cpu().numpy(), hist.x_filt.cpu().numpy()
+  hP_p, hP_f = hist.P_pred.cpu().numpy(), hist.P_filt.cpu().numpy()
+  t = hist.t.cpu().numpy()
+  for b in range(0, B, 7):
+    xr, Pr = rts_smooth(o, hx_p[:, b], hx_f[:, b], hP_p[:, b], hP_f[:, b], t, 2, 2)
+    assert rel_err(xs[:, b], xr) < 1e-9 and rel_err(Ps[:, b], Pr) < 1e-9
