@@ -254,6 +254,39 @@ def run_gpu(args):
   d2h = streamer.d2h_bytes / e2e_steps
   assert bool(torch.isfinite(streamer.x_host[0]).all())
 
+  # ---- the stateless C-ABI entry point with HOST buffers: <name>_host_step_<kind>(x, P, Q, ..., z, R, ...) copies the
+  #      whole state in and out (what calling the reference's <name>_predict + <name>_update_<k> on caller-owned
+  #      host arrays does); PCIe-bound by construction (2 x (EDIM^2 + DIM) doubles per filter-step) ----
+  host_abi = None
+  if rank == 0:
+    try:
+      Bh = min(B, 131072)
+      kind_h = sched[args.warmup + 1]
+      ffi, lib = eng._ffi, eng._lib
+      hx = eng.x[:Bh].cpu().pin_memory()
+      hP = eng.P[:Bh].cpu().pin_memory()
+      hzz = hz[kind_h][0][:Bh].clone().pin_memory()
+      hRR = torch.as_tensor(pools[kind_h][1][:Bh]).contiguous().pin_memory()
+      Qh = torch.as_tensor(np.ascontiguousarray(Q)).pin_memory()
+      qi = ffi.new("int[]", list(quat) or [0])
+      fn = getattr(lib, f"{fname}_host_step_{kind_h}")
+      pp = lambda t: ffi.cast("double *", t.data_ptr())
+      def host_call():
+        fn(pp(hx), pp(hP), ffi.cast("const double *", Qh.data_ptr()), ffi.NULL, 0.01, pp(hzz), ffi.cast("const double *", hRR.data_ptr()),
+           ffi.NULL, 1, Bh, qi, len(quat), eng.flags)
+      host_call()
+      t_h = time.perf_counter()
+      n_h = 5
+      for _ in range(n_h):
+        host_call()                       # synchronous: returns when the results are back in the host arrays
+      dt_h = (time.perf_counter() - t_h) / n_h
+      host_abi = {"value": Bh / dt_h, "unit": "steps/s", "filters": Bh, "ms_per_call": dt_h * 1e3,
+                  "h2d_bytes_per_step": 8 * Bh * (dim + edim * edim + zdim[kind_h] + zdim[kind_h]**2),
+                  "d2h_bytes_per_step": 8 * Bh * (dim + edim * edim + zdim[kind_h]),
+                  "what": f"{fname}_host_step_{kind_h}: x, P, z, R in pinned HOST memory in, x, P, y out, every call (chunked over 3 streams inside the library)"}
+    except Exception as ex:  # pylint: disable=broad-except
+      host_abi = {"error": repr(ex)[:200]}
+
   # ---- final gather of the state estimates (the only collective of the system) ----
   gather_ms = None
   if world > 1:
@@ -302,6 +335,8 @@ def run_gpu(args):
               "steps": e2e_steps, "what": "HostStreamer.submit(t, kind, z_pinned_host, R_kind): H2D of z, fused step, D2H of x and y into pinned host memory EVERY step (3 streams overlap consecutive steps); P stays resident"},
       "clocks": clocks.summary(),
     }
+    if host_abi is not None:
+      line["e2e_stateless_host_c_abi"] = host_abi
     if gather_ms is not None:
       line["final_gather_ms"] = gather_ms
     if not args.no_cpu_baseline and world == 1:
