@@ -47,6 +47,15 @@ namespace rnb {
 #ifndef RNB_STAGES
 #define RNB_STAGES 1   // covariance tile ring per warp = bulk loads in flight per warp
 #endif
+#ifndef RNB_QDIAG_ASM
+#define RNB_QDIAG_ASM 1
+#endif
+#ifndef RNB_EX128
+#define RNB_EX128 1
+#endif
+#ifndef RNB_FV_EARLY
+#define RNB_FV_EARLY 0   // 1: F value slots are loaded before the tile wait -- measured: 74 more live registers, spills inside the per-filter loop
+#endif
 #ifndef RNB_TMA_STORE
 #define RNB_TMA_STORE 0  // 1: results leave through the tile with a bulk store; 0: plain coalesced stores from registers
 #endif
@@ -124,7 +133,10 @@ struct WarpScratch {
   alignas(128) double tile[(NST > 0 ? NST : 1) * (use_tma<M>() ? M::EDIM * M::EDIM : 2)];  // covariance tiles (TMA ring)
   alignas(8) uint64_t full[NST > 0 ? NST : 1];                                              // "tile landed" mbarriers
   alignas(16) double rows[G * L::STRIDE];
-  static constexpr int EXS = M::EDIM | 1;                        // exchange row stride (odd: conflict-free column writes)
+  // exchange row stride = 2 (mod 4) doubles: rows start 16-byte aligned and the lanes that read a whole row each
+  // (128-bit accesses, one row per lane) hit distinct bank groups; the column writes (lane l -> element l) are
+  // conflict free for any stride
+  static constexpr int EXS = ((M::EDIM + 3) & ~3) + 2;
   static constexpr int EXN = (M::NFROWS > 0 ? M::NFROWS : 1) * EXS + 32;
   static constexpr int HPN = K::ZDIM * 32;
   // one buffer, two lives: row exchange for F P F^T during the predict, then (H P)[c][k] during the update
@@ -161,6 +173,38 @@ __device__ __forceinline__ void stage_in(const double* __restrict__ g, double* r
     const int idx = it * 32 + lane;
     const int f = idx / WD, i = idx - f * WD;
     if (idx < ng * WD) rows[f * STRIDE + off + i] = v[it];
+  }
+}
+// the two halves of stage_in / gather_in as separate calls, so that the kernel can put the loads of SEVERAL record
+// types (x, z, R) in flight before the first dependent shared-memory store: one global round trip per group
+template <int WD, int G>
+struct StageRegs { static constexpr int NIT = (G * WD + 31) / 32; double v[NIT]; };
+template <int WD, int G>
+__device__ __forceinline__ void stage_load(const double* __restrict__ g, StageRegs<WD, G>& r, int ng, int lane) {
+#pragma unroll
+  for (int it = 0; it < StageRegs<WD, G>::NIT; ++it) {
+    const int idx = it * 32 + lane;
+    r.v[it] = (idx < ng * WD) ? g[idx] : 0.0;
+  }
+}
+template <int WD, int G>
+__device__ __forceinline__ void gather_load(const double* __restrict__ g, StageRegs<WD, G>& r, int ng, int lane, long long myfid) {
+#pragma unroll
+  for (int it = 0; it < StageRegs<WD, G>::NIT; ++it) {
+    const int idx = it * 32 + lane;
+    const bool ok = idx < ng * WD;
+    const int f = ok ? idx / WD : 0, i = idx - f * WD;
+    const long long fid = __shfl_sync(0xffffffffu, myfid, f);
+    r.v[it] = ok ? g[fid * WD + i] : 0.0;
+  }
+}
+template <int WD, int STRIDE, int G>
+__device__ __forceinline__ void stage_store(const StageRegs<WD, G>& r, double* rows, int off, int ng, int lane) {
+#pragma unroll
+  for (int it = 0; it < StageRegs<WD, G>::NIT; ++it) {
+    const int idx = it * 32 + lane;
+    const int f = idx / WD, i = idx - f * WD;
+    if (idx < ng * WD) rows[f * STRIDE + off + i] = r.v[it];
   }
 }
 template <int WD, int STRIDE>
@@ -279,27 +323,45 @@ __global__ void __launch_bounds__(W * 32, RNB_MIN_WARPS / W) ekf_step_warp(const
     }
 
     // ---- stage this group's small per-filter records into the rows (coalesced) ----
-    if (o == 0) {
-      if (gathered) gather_in<D, RS, G>(a.x, s.rows, L::OFF_X, ng, lane, myfid);
-      else stage_in<D, RS, G>(a.x + b0 * D, s.rows, L::OFF_X, ng, lane);
-    }
-    if constexpr (UPD) {
-      const bool shared_R = a.flags & FLAG_SHARED_R;
-      if (a.n_obs == 1) {
-        stage_in<Z, RS, G>(a.z + b0 * Z, s.rows, L::OFF_Y, ng, lane);
-        if (!shared_R) stage_in<Z * Z, RS, G>(a.R + b0 * (Z * Z), s.rows, L::OFF_R, ng, lane);
-      } else if (mine) {
-        const long long bo = (b0 + lane) * a.n_obs + o;
-#pragma unroll
-        for (int i = 0; i < Z; ++i) myrow[L::OFF_Y + i] = a.z[bo * Z + i];
-        if (!shared_R) {
-#pragma unroll
-          for (int i = 0; i < Z * Z; ++i) myrow[L::OFF_R + i] = a.R[bo * (Z * Z) + i];
+    // every global load of the block (x, z, R, dt) is issued before the first shared-memory store that depends on
+    // one of them: the group pays ONE global round trip here instead of one per record type (profiles/r01_f: four
+    // serialised long-scoreboard waits = 10 % of the kernel's samples)
+    double dt_lane = a.dt;
+    {
+      StageRegs<D, G> rx;
+      StageRegs<Z, G> rz;
+      StageRegs<Z * Z, G> rR;
+      const bool shared_R = UPD && (a.flags & FLAG_SHARED_R);
+      const bool bulk_obs = UPD && a.n_obs == 1;
+      if (o == 0) {
+        if (gathered) gather_load<D, G>(a.x, rx, ng, lane, myfid);
+        else stage_load<D, G>(a.x + b0 * D, rx, ng, lane);
+      }
+      if constexpr (UPD) {
+        if (bulk_obs) {
+          stage_load<Z, G>(a.z + b0 * Z, rz, ng, lane);
+          if (!shared_R) stage_load<Z * Z, G>(a.R + b0 * (Z * Z), rR, ng, lane);
         }
       }
-      if (shared_R && mine) {
+      if (do_pred && mine && a.dt_arr) dt_lane = a.dt_arr[b0 + lane];
+      if (o == 0) stage_store<D, RS, G>(rx, s.rows, L::OFF_X, ng, lane);
+      if constexpr (UPD) {
+        if (bulk_obs) {
+          stage_store<Z, RS, G>(rz, s.rows, L::OFF_Y, ng, lane);
+          if (!shared_R) stage_store<Z * Z, RS, G>(rR, s.rows, L::OFF_R, ng, lane);
+        } else if (mine) {
+          const long long bo = (b0 + lane) * a.n_obs + o;
 #pragma unroll
-        for (int i = 0; i < Z * Z; ++i) myrow[L::OFF_R + i] = __ldg(a.R + i);
+          for (int i = 0; i < Z; ++i) myrow[L::OFF_Y + i] = a.z[bo * Z + i];
+          if (!shared_R) {
+#pragma unroll
+            for (int i = 0; i < Z * Z; ++i) myrow[L::OFF_R + i] = a.R[bo * (Z * Z) + i];
+          }
+        }
+        if (shared_R && mine) {
+#pragma unroll
+          for (int i = 0; i < Z * Z; ++i) myrow[L::OFF_R + i] = __ldg(a.R + i);
+        }
       }
     }
     __syncwarp();
@@ -309,7 +371,7 @@ __global__ void __launch_bounds__(W * 32, RNB_MIN_WARPS / W) ekf_step_warp(const
       double xp[L::Dp];
       vec_load(myrow + L::OFF_X, xp);
       if (do_pred) {
-        const double dt = a.dt_arr ? a.dt_arr[b0 + lane] : a.dt;
+        const double dt = dt_lane;
         double fv[L::NFp];
         double xn[L::Dp];
         M::predict_leaf(xp, dt, a.gv, xn, fv);
@@ -356,6 +418,9 @@ __global__ void __launch_bounds__(W * 32, RNB_MIN_WARPS / W) ekf_step_warp(const
       double p[E];
       const uint32_t slot = it % NST;
       double* tile = s.tile + (TMA ? slot * (E * E) : 0);
+      // the F value slots do not depend on the tile: their (broadcast) loads go out before the wait
+      double fv[L::NFp];
+      if (RNB_FV_EARLY && do_pred) vec_load(row + L::OFF_FV, fv);
       if constexpr (TMA) {
         mbar_wait(&s.full[slot], (it / NST) & 1u);
         // P is symmetric: read ROW `lane` (contiguous, 128-bit accesses) as column `lane`
@@ -391,8 +456,7 @@ __global__ void __launch_bounds__(W * 32, RNB_MIN_WARPS / W) ekf_step_warp(const
       ++it;
 
       if (do_pred) {
-        double fv[L::NFp];
-        vec_load(row + L::OFF_FV, fv);
+        if (!RNB_FV_EARLY) vec_load(row + L::OFF_FV, fv);
         const double dt = row[L::OFF_DT];
         // rows of F P that are not rows of P (F's non-identity rows) go through the exchange; every other
         // row j of F P equals column j of P (symmetry), which the lane already holds
@@ -409,8 +473,17 @@ __global__ void __launch_bounds__(W * 32, RNB_MIN_WARPS / W) ekf_step_warp(const
           const int slot_rf = __popc(M::FROW_MASK & ((1u << lane) - 1u));
           if (in_rf) {  // this lane's row of F P replaces its column of P
             const double* xr = s.exhp + slot_rf * EXS;
+            if constexpr (RNB_EX128) {
 #pragma unroll
-            for (int i = 0; i < E; ++i) p[i] = xr[i];
+              for (int i = 0; i + 1 < E; i += 2) {
+                const double2 t = *reinterpret_cast<const double2*>(xr + i);
+                p[i] = t.x; p[i + 1] = t.y;
+              }
+              if constexpr (E % 2) p[E - 1] = xr[E - 1];
+            } else {
+#pragma unroll
+              for (int i = 0; i < E; ++i) p[i] = xr[i];
+            }
           }
           M::F_apply(fv, p);                        // column `lane` of F (F P)^T = F P F^T
           __syncwarp();
@@ -420,8 +493,11 @@ __global__ void __launch_bounds__(W * 32, RNB_MIN_WARPS / W) ekf_step_warp(const
         if (a.flags & FLAG_Q_DIAG) {
           // diagonal process noise: only P[lane][lane] changes
           const double dq = dt * qdiag;
+          // one predicated DADD per element (a select costs ISETP + 2 FSEL + DADD; an `if` compiles to branches)
 #pragma unroll
-          for (int i = 0; i < E; ++i) p[i] += (i == lane) ? dq : 0.0;
+          for (int i = 0; i < E; ++i)
+            if constexpr (!RNB_QDIAG_ASM) p[i] += (i == lane) ? dq : 0.0; else
+            asm("{\n .reg .pred q;\n setp.eq.s32 q, %2, %3;\n @q add.f64 %0, %0, %1;\n}" : "+d"(p[i]) : "d"(dq), "r"(lane), "r"(i));
         } else {
           const double* Qg = a.Q + col;
 #pragma unroll
