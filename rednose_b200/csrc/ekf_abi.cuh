@@ -8,7 +8,7 @@
 #pragma once
 #include "ekf_common.cuh"
 #include "ekf_thread.cuh"
-#include "ekf_warp.cuh"
+#include "ekf_warp2.cuh"
 #include "ekf_cta.cuh"
 #include "ekf_rts.cuh"
 #include "ekf_rts_mma.cuh"
@@ -68,29 +68,63 @@ inline void launch_step(const StepArgs<M::NG>& a, cudaStream_t st) {
       last_status() = (int)cudaErrorMisalignedAddress;
       return;
     }
-    constexpr int G = RNB_GROUP, W = RNB_WARPS;
-    constexpr size_t smem = warp_smem_bytes<M, K, G, W>();
-    const long long per_cta = (long long)G * W;
-    const unsigned grid = (unsigned)((a.B + per_cta - 1) / per_cta);
-    auto run = [&](void (*kern)(const StepArgs<M::NG>)) {
-      static std::unordered_set<const void*> configured;  // kernels share one pointer type: key by address
-      if (configured.insert((const void*)kern).second) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      }
-      kern<<<grid, W * 32, smem, st>>>(a);
-    };
-    if constexpr (PRED && UPD) {
-      // the gather-list variant exists only for the fused step (what the ragged scheduler issues)
-      if (a.idx) run(ekf_step_warp<M, K, PRED, UPD, G, W, true>);
-      else run(ekf_step_warp<M, K, PRED, UPD, G, W, false>);
-    } else {
-      if (a.idx) {
-        fprintf(stderr, "[rednose_b200] gather lists are only supported by the fused predict+update step\n");
-        last_status() = (int)cudaErrorNotSupported;
+    bool paired = false;
+    if constexpr (use_pair<M>()) paired = pair_enabled();
+    if constexpr (use_pair<M>()) if (paired) {
+      // two filters per warp (ekf_warp2.cuh): 128-bit accesses to every covariance array
+      if ((reinterpret_cast<uintptr_t>(a.hP_pred) | reinterpret_cast<uintptr_t>(a.hP_filt)) & 15u) {
+        fprintf(stderr, "[rednose_b200] covariance history slabs must be 16-byte aligned\n");
+        last_status() = (int)cudaErrorMisalignedAddress;
         return;
       }
-      run(ekf_step_warp<M, K, PRED, UPD, G, W, false>);
+      constexpr int G = RNB_PAIR_GROUP;
+      constexpr size_t smem = pair_smem_bytes<M, K, G>();
+      const unsigned grid = (unsigned)((a.B + G - 1) / G);
+      auto run = [&](void (*kern)(const StepArgs<M::NG>)) {
+        static std::unordered_set<const void*> configured;
+        if (configured.insert((const void*)kern).second) {
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+        kern<<<grid, 32, smem, st>>>(a);
+      };
+      if constexpr (PRED && UPD) {
+        if (a.idx) run(ekf_step_pair<M, K, PRED, UPD, G, true>);
+        else run(ekf_step_pair<M, K, PRED, UPD, G, false>);
+      } else {
+        if (a.idx) {
+          fprintf(stderr, "[rednose_b200] gather lists are only supported by the fused predict+update step\n");
+          last_status() = (int)cudaErrorNotSupported;
+          return;
+        }
+        run(ekf_step_pair<M, K, PRED, UPD, G, false>);
+      }
+    }
+    if (!paired) {
+      constexpr int G = RNB_GROUP, W = RNB_WARPS;
+      constexpr size_t smem = warp_smem_bytes<M, K, G, W>();
+      const long long per_cta = (long long)G * W;
+      const unsigned grid = (unsigned)((a.B + per_cta - 1) / per_cta);
+      auto run = [&](void (*kern)(const StepArgs<M::NG>)) {
+        static std::unordered_set<const void*> configured;  // kernels share one pointer type: key by address
+        if (configured.insert((const void*)kern).second) {
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+        kern<<<grid, W * 32, smem, st>>>(a);
+      };
+      if constexpr (PRED && UPD) {
+        // the gather-list variant exists only for the fused step (what the ragged scheduler issues)
+        if (a.idx) run(ekf_step_warp<M, K, PRED, UPD, G, W, true>);
+        else run(ekf_step_warp<M, K, PRED, UPD, G, W, false>);
+      } else {
+        if (a.idx) {
+          fprintf(stderr, "[rednose_b200] gather lists are only supported by the fused predict+update step\n");
+          last_status() = (int)cudaErrorNotSupported;
+          return;
+        }
+        run(ekf_step_warp<M, K, PRED, UPD, G, W, false>);
+      }
     }
   } else {
     launch_step_cta<M, K, PRED, UPD>(a, st);
