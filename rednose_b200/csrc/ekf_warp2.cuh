@@ -31,6 +31,9 @@ namespace rnb {
 #ifndef RNB_PAIR_MIN_WARPS
 #define RNB_PAIR_MIN_WARPS 8
 #endif
+#ifndef RNB_PAIR_TMA_STAGE
+#define RNB_PAIR_TMA_STAGE 1   // x / z / R / dt blocks of a full group arrive by bulk copy (one mbarrier wait, no registers held)
+#endif
 
 template <class M, class K, int G>
 struct PairScratch {
@@ -42,10 +45,23 @@ struct PairScratch {
   alignas(16) double rows[G * L::STRIDE];
   static constexpr int EXS = ((E + 3) & ~3) + 2;      // exchange row stride, = 2 (mod 4): see WarpScratch
   static constexpr int HPS = 32;                      // (H P)[c][k] row stride
-  static constexpr int EXN = (M::NFROWS > 0 ? M::NFROWS : 1) * EXS + 32;
+  // exchange row of slot s: every 8th row is skewed by 16 bytes -- with a stride = 2 (mod 4) doubles, rows s and s+8
+  // would start in the same bank group, and the lanes that read one whole row each hold rows 0, 2, 4, 6, 8 (live_kf)
+  static constexpr int exrow(int sl) { return sl * EXS + 2 * (sl >> 3); }
+  static constexpr int EXN = exrow(M::NFROWS > 0 ? M::NFROWS : 1) + 32;
   static constexpr int HPN = K::ZDIM * HPS;
-  static constexpr int XN = ((EXN > HPN ? EXN : HPN) + 3) & ~1;   // per half; = odd multiple of 2 keeps the halves on different banks
+  // staging area for the group's x / z / R / dt blocks (bulk-copied, consumed by phase A before the exchange
+  // buffers come into use): offsets in doubles, each 16-byte aligned
+  static constexpr int STG_X = 0;
+  static constexpr int STG_Z = STG_X + even_up(G * M::DIM);
+  static constexpr int STG_R = STG_Z + even_up(G * K::ZDIM);
+  static constexpr int STG_DT = STG_R + even_up(G * K::ZDIM * K::ZDIM);
+  static constexpr int STG_N = STG_DT + even_up(G);
+  static constexpr int XN0 = ((EXN > HPN ? EXN : HPN) + 3) & ~1;  // per half
+  static constexpr int XN1 = (STG_N + 1) / 2;
+  static constexpr int XN = (((XN0 > XN1 ? XN0 : XN1) + 1) & ~1) | 2;   // even, = 2 (mod 4): the halves sit on different banks
   alignas(16) double exhp[2 * XN];
+  alignas(8) uint64_t stg;                            // "staging blocks landed" mbarrier
 };
 
 template <class M, class K, bool PRED, bool UPD, int G, bool GATHER>
@@ -53,7 +69,7 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
   constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM;
   using L = RowLayout<M, K>;
   using SC = PairScratch<M, K, G>;
-  constexpr int RS = L::STRIDE, EXS = SC::EXS, HPS = SC::HPS, XN = SC::XN;
+  constexpr int RS = L::STRIDE, HPS = SC::HPS, XN = SC::XN;
   static_assert(E <= 32 && E % 2 == 0, "pair kernel: even EDIM <= 32");
   static_assert(G <= 32 && G % 2 == 0, "group size");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -66,7 +82,7 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
   const int h = lane >> 4;                  // half-warp = which filter of the pair
   const int hl_raw = lane & 15;
   const bool act = hl_raw < E / 2;          // lane owns two real columns
-  const int hl = act ? hl_raw : 0;
+  const int hl = act ? hl_raw : E / 2 - 1;  // idle lanes mirror the last active lane (same quarter-warp: a broadcast, not a bank conflict)
   const int c0 = 2 * hl;                    // owned columns c0, c0 + 1
   double* myrow = s.rows + (lane < G ? lane : 0) * RS;
   const bool mine = lane < ng;
@@ -84,6 +100,7 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
   if (lane == 0) {
 #pragma unroll
     for (int st = 0; st < NST; ++st) mbar_init(&s.full[st], 1);
+    mbar_init(&s.stg, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -118,9 +135,48 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
       if (lane == 0 && 2 * k < ng) issue_pair(2 * k, (it + k) % NST, fa, fb);
     }
 
-    // ---- stage x, z, R, dt of the group: every global load before the first dependent store (one round trip) ----
+    // ---- stage x, z, R, dt of the group ----
     double dt_lane = a.dt;
-    {
+    bool staged = false;
+    if constexpr (RNB_PAIR_TMA_STAGE && !GATHER) {
+      // full group, 16-byte aligned arrays, one observation per filter: the blocks are contiguous -> bulk copies into
+      // the (still idle) exchange buffers, one mbarrier wait; used at most once per kernel (o == 0), so parity 0
+      const bool ok = o == 0 && ng == G && (!UPD || a.n_obs == 1) &&
+          !((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.z) | reinterpret_cast<uintptr_t>(a.R) |
+             reinterpret_cast<uintptr_t>(a.dt_arr)) & 15u);
+      if (ok) {
+        staged = true;
+        const bool shared_R = UPD && (a.flags & FLAG_SHARED_R);
+        const bool want_dt = do_pred && a.dt_arr;
+        double* stg = s.exhp;
+        if (lane == 0) {
+          uint32_t bytes = G * D * 8;
+          if (UPD) bytes += G * Z * 8 + (shared_R ? 0 : G * Z * Z * 8);
+          if (want_dt) bytes += G * 8;
+          mbar_expect_tx(&s.stg, bytes);
+          tma_load_1d(stg + SC::STG_X, a.x + b0 * D, G * D * 8, &s.stg);
+          if (UPD) {
+            tma_load_1d(stg + SC::STG_Z, a.z + b0 * Z, G * Z * 8, &s.stg);
+            if (!shared_R) tma_load_1d(stg + SC::STG_R, a.R + b0 * (Z * Z), G * Z * Z * 8, &s.stg);
+          }
+          if (want_dt) tma_load_1d(stg + SC::STG_DT, a.dt_arr + b0, G * 8, &s.stg);
+        }
+        mbar_wait(&s.stg, 0);
+        if (mine) {   // ng == G: every lane < G owns a record; odd record strides -> conflict-free lane-strided reads
+#pragma unroll
+          for (int i = 0; i < D; ++i) myrow[L::OFF_X + i] = stg[SC::STG_X + lane * D + i];
+          if constexpr (UPD) {
+#pragma unroll
+            for (int i = 0; i < Z; ++i) myrow[L::OFF_Y + i] = stg[SC::STG_Z + lane * Z + i];
+#pragma unroll
+            for (int i = 0; i < Z * Z; ++i) myrow[L::OFF_R + i] = shared_R ? __ldg(a.R + i) : stg[SC::STG_R + lane * (Z * Z) + i];
+          }
+          if (want_dt) dt_lane = stg[SC::STG_DT + lane];
+        }
+      }
+    }
+    if (!staged) {
+      // register path: every global load of the block before the first dependent shared-memory store
       StageRegs<D, G> rx;
       StageRegs<Z, G> rz;
       StageRegs<Z * Z, G> rR;
@@ -245,7 +301,7 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
 #pragma unroll
               for (int r = 0; r < E; ++r) {
                 if ((M::FROW_MASK >> r) & 1u) {
-                  *reinterpret_cast<double2*>(exh + sl * EXS + c0) = make_double2(m0[r], m1[r]);
+                  *reinterpret_cast<double2*>(exh + SC::exrow(sl) + c0) = make_double2(m0[r], m1[r]);
                   ++sl;
                 }
               }
@@ -254,12 +310,12 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
           __syncwarp();
           // a column whose index is a non-identity row of F is replaced by that row of F P (symmetry gives the rest)
           if ((M::FROW_MASK >> c0) & 1u) {
-            const double* xr = exh + __popc(M::FROW_MASK & ((1u << c0) - 1u)) * EXS;
+            const double* xr = exh + SC::exrow(__popc(M::FROW_MASK & ((1u << c0) - 1u)));
 #pragma unroll
             for (int i = 0; i < E; ++i) p0[i] = xr[i];   // 64-bit loads: p0[i] shares a register quad with p1[i], not p0[i+1]
           }
           if ((M::FROW_MASK >> (c0 + 1)) & 1u) {
-            const double* xr = exh + __popc(M::FROW_MASK & ((2u << c0) - 1u)) * EXS;
+            const double* xr = exh + SC::exrow(__popc(M::FROW_MASK & ((2u << c0) - 1u)));
 #pragma unroll
             for (int i = 0; i < E; ++i) p1[i] = xr[i];
           }
