@@ -313,6 +313,12 @@ def run_gpu(args):
         traffic = tj.get(f"ekf_step<{fname}, kind {dom}>")
     except Exception:  # pylint: disable=broad-except
       pass
+    if edim <= 6:
+      kern = "ekf_step_thread"
+    elif edim <= 32:
+      kern = "ekf_step_pair" if (edim % 2 == 0 and not os.environ.get("REDNOSE_B200_WARP_KERNEL", "").startswith("s")) else "ekf_step_warp"
+    else:
+      kern = "ekf_step_cta"
     total_steps = B * args.steps * world
     line = {
       "metric": "fused EKF predict+update steps/s (batched, float64)",
@@ -328,7 +334,7 @@ def run_gpu(args):
                  "sharding": "independent filters per GPU, no data-path collective"},
       "gpu_launches": launches,
       "per_kind_ms": {str(k): float(np.mean(v)) for k, v in per_kind.items()},
-      "roofline": {"bound": "hbm", "kernel": f"ekf_step<{fname}, kind {dom}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+      "roofline": {"bound": "hbm", "kernel": f"{kern}<{fname}, kind {dom}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                    "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_step": bytes_per_step(dim, edim, zdim[dom]), "algorithmic_bytes_per_launch": algo,
                    "traffic": traffic},
       "e2e": {"value": B * e2e_steps * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -31,6 +31,9 @@ namespace rnb {
 #ifndef RNB_PAIR_MIN_WARPS
 #define RNB_PAIR_MIN_WARPS 8
 #endif
+#ifndef RNB_PAIR_FV_EARLY
+#define RNB_PAIR_FV_EARLY 0    // 1: F value slots are fetched before the tile wait instead of after it
+#endif
 #ifndef RNB_PAIR_TMA_STAGE
 #define RNB_PAIR_TMA_STAGE 1   // x / z / R / dt blocks of a full group arrive by bulk copy (one mbarrier wait, no registers held)
 #endif
@@ -268,6 +271,8 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
       const uint32_t slot = it % NST;
       const double* tile = s.tile + slot * (2 * E * E) + (valid ? h : 0) * (E * E);
       double p0[E], p1[E];                        // columns c0 and c0 + 1
+      double fv[L::NFp];
+      if (RNB_PAIR_FV_EARLY && do_pred) vec_load(row + L::OFF_FV, fv);
 
       mbar_wait(&s.full[slot], (it / NST) & 1u);
       // row i of the tile holds P[i][c0], P[i][c0+1] side by side: one 128-bit load per row feeds both columns
@@ -285,8 +290,7 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
       ++it;
 
       if (do_pred) {
-        double fv[L::NFp];
-        vec_load(row + L::OFF_FV, fv);
+        if (!RNB_PAIR_FV_EARLY) vec_load(row + L::OFF_FV, fv);
         const double dt = row[L::OFF_DT];
         if constexpr (M::NFROWS > 0) {
           {
