@@ -274,9 +274,10 @@ template <class M>
 inline void single_predict(HostCtx<M>& ctx, double* x, double* P, const double* Q, double dt) {
   constexpr int D = M::DIM, E = M::EDIM;
   std::lock_guard<std::mutex> lk(ctx.mu);
-  double* d = ctx.scratch(D + 2 * E * E);
+  constexpr int DA = (D + 1) & ~1;   // P starts 16-byte aligned behind x (covariance tiles move by bulk copy / 128-bit accesses)
+  double* d = ctx.scratch(DA + 2 * E * E);
   if (!d) return;
-  double* dx = d; double* dP = d + D; double* dQ = dP + E * E;
+  double* dx = d; double* dP = d + DA; double* dQ = dP + E * E;
   if (!check(cudaMemcpy(dx, x, sizeof(double) * D, cudaMemcpyHostToDevice), "memcpy x")) return;
   cudaMemcpy(dP, P, sizeof(double) * E * E, cudaMemcpyHostToDevice);
   cudaMemcpy(dQ, Q, sizeof(double) * E * E, cudaMemcpyHostToDevice);
@@ -292,9 +293,10 @@ template <class M, class K>
 inline void single_update(HostCtx<M>& ctx, double* x, double* P, double* z, const double* R, const double* ea) {
   constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM, EA = K::EADIM;
   std::lock_guard<std::mutex> lk(ctx.mu);
-  double* d = ctx.scratch(D + E * E + Z + Z * Z + (EA > 0 ? EA : 1));
+  constexpr int DA = (D + 1) & ~1;   // see single_predict
+  double* d = ctx.scratch(DA + E * E + Z + Z * Z + (EA > 0 ? EA : 1));
   if (!d) return;
-  double* dx = d; double* dP = d + D; double* dz = dP + E * E; double* dR = dz + Z; double* dea = dR + Z * Z;
+  double* dx = d; double* dP = d + DA; double* dz = dP + E * E; double* dR = dz + Z; double* dea = dR + Z * Z;
   if (!check(cudaMemcpy(dx, x, sizeof(double) * D, cudaMemcpyHostToDevice), "memcpy x")) return;
   cudaMemcpy(dP, P, sizeof(double) * E * E, cudaMemcpyHostToDevice);
   cudaMemcpy(dz, z, sizeof(double) * Z, cudaMemcpyHostToDevice);

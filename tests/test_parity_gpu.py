@@ -515,3 +515,43 @@ def test_pair_and_single_kernels_agree_to_rounding(gen_dir, oracle_dir, monkeypa
     y = e.step(10, 0.01, z, R)
     out.append((e.state().copy(), e.covs().copy(), y.cpu().numpy().copy()))
   assert rel_err(out[0][0], out[1][0]) < 1e-14 and rel_err(out[0][1], out[1][1]) < 1e-14 and rel_err(out[0][2], out[1][2]) < 1e-14
+
+
+def test_dense_process_noise(gen_dir, oracle_dir):
+  """A Q with off-diagonal terms takes the dense dt*Q path of the kernels (the diagonal fast path is what every
+  other live test runs, examples/live_kf.py's Q being diagonal); ekf_c.c:27-28."""
+  o = Oracle(oracle_dir, "live")
+  B = 131
+  x, P, Qm = live_batch(B, seed=17)
+  A = np.random.default_rng(4).normal(size=(22, 22)) * 1e-3
+  Qd = Qm + A @ A.T
+  z, R = live_obs(o, 4, x)
+  xr, Pr, yr = o.batch_step(4, x, P, Qd, 0.01, z, R, quat_idxs=[3], flags=3)
+  e = _engine(gen_dir, "live", x, P, Qd, quaternion_idxs=[3])
+  y = e.step(4, 0.01, z, R)
+  assert rel_err(e.state(), xr) < TIGHT and rel_err(e.covs(), Pr) < TIGHT and rel_err(y.cpu().numpy()[:, 0], yr) < TIGHT
+
+
+def test_live_single_filter_dropin_path(gen_dir, oracle_dir):
+  """The reference's own calling pattern on the 23-state filter: one filter, host arrays, `live_predict` +
+  `live_update_<k>` through both drivers (native EKF_sym_pyx and the Python EKF_sym), CUDA library against the
+  reference-generated CPU library on the same stream (rednose/helpers/ekf_sym.py:258-343, ekf_sym.cc:125-215)."""
+  from rednose_b200.ekf_sym import EKF_sym
+  from rednose_b200.filters.live import LiveKalman, ObservationKind as K
+  for filter_cls in (None, EKF_sym):
+    gpu, cpu = LiveKalman(gen_dir, filter_cls), LiveKalman(oracle_dir, filter_cls)
+    rng = np.random.default_rng(3)
+    t = 0.0
+    for k in range(40):
+      t += 0.01
+      if k % 10 == 0:
+        kind, data = K.ECEF_POS, [cpu.x[:3] + rng.normal(0, 1.0, 3)]
+      elif k % 10 == 5:
+        kind, data = K.CAMERA_ODO_TRANSLATION, [np.concatenate([rng.normal(0, 0.1, 3), [0.1, 0.1, 0.1]])]
+      elif k % 10 == 7:
+        kind, data = K.ODOMETRIC_SPEED, [[0.0]]
+      else:
+        kind, data = (K.PHONE_GYRO if k % 2 else K.PHONE_ACCEL), [rng.normal(0, 0.01, 3) + (0.0 if k % 2 else np.array([0, 0, -9.8]))]
+      rg, rc = gpu.predict_and_observe(t, kind, data), cpu.predict_and_observe(t, kind, data)
+      assert rg is not None and rc is not None
+      assert rel_err(gpu.x, cpu.x) < TOL and rel_err(gpu.P, cpu.P) < TOL, (k, int(kind))   # contract: 1e-6
