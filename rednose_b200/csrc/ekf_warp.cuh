@@ -1,6 +1,9 @@
 // rednose_b200 -- warp-per-filter fused predict+update kernel (6 < EDIM <= 32,
 // e.g. live_kf: DIM 23 / EDIM 22, examples/live_kf.py:97-124).
 //
+// Since the end of round 1 even-EDIM filters run ekf_step_pair (ekf_warp2.cuh: two filters per warp, same phases and
+// arithmetic, built on the primitives of this file); this kernel serves odd EDIM and REDNOSE_B200_WARP_KERNEL=single.
+//
 // A warp owns a GROUP of G consecutive filters and walks through three phases:
 //
 //  A  (thread-per-filter)  lane l evaluates the generated leaf code of filter l of the group:
@@ -38,9 +41,6 @@ namespace rnb {
 #define RNB_WARPS 1    // warps per CTA (warps never synchronise with each other)
 #endif
 
-#ifndef RNB_STAGE_BATCHED
-#define RNB_STAGE_BATCHED 1   // staging of x / z / R: issue every load of the block before the first store
-#endif
 #ifndef RNB_TMA
 #define RNB_TMA 1      // stage covariance tiles through shared memory with cp.async.bulk (TMA) load + store
 #endif
@@ -149,34 +149,11 @@ __device__ __forceinline__ void lane_normalize(double* xs, const StepArgs<NG>& a
   for (int q = 0; q < a.n_quat; ++q) normalize4(xs + a.quat_idx[q]);
 }
 
-// cooperative, coalesced copy between a contiguous global block of ng records of width WD and the
-// per-filter rows in shared memory (record f -> rows[f * STRIDE + off .. + WD))
-template <int WD, int STRIDE, int G>
-__device__ __forceinline__ void stage_in(const double* __restrict__ g, double* rows, int off, int ng, int lane) {
-  // all loads first, then all stores: one global-latency round trip for the whole block instead of one per pass
-#if !RNB_STAGE_BATCHED
-  for (int idx = lane; idx < ng * WD; idx += 32) {
-    const int f = idx / WD, i = idx - f * WD;
-    rows[f * STRIDE + off + i] = g[idx];
-  }
-  return;
-#endif
-  constexpr int NIT = (G * WD + 31) / 32;
-  double v[NIT];
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int idx = it * 32 + lane;
-    v[it] = (idx < ng * WD) ? g[idx] : 0.0;
-  }
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int idx = it * 32 + lane;
-    const int f = idx / WD, i = idx - f * WD;
-    if (idx < ng * WD) rows[f * STRIDE + off + i] = v[it];
-  }
-}
-// the two halves of stage_in / gather_in as separate calls, so that the kernel can put the loads of SEVERAL record
-// types (x, z, R) in flight before the first dependent shared-memory store: one global round trip per group
+// Cooperative, coalesced copies between a contiguous global block of ng records of width WD and the per-filter
+// rows in shared memory (record f -> rows[f * STRIDE + off .. + WD)).  The inbound direction is split into a load
+// half and a store half so that the kernel can put the loads of SEVERAL record types (x, z, R) in flight before the
+// first dependent shared-memory store: one global round trip per group.  gather_load is the same for records
+// scattered in global memory: record f lives at g + fid(f) * WD, fid held by lane f.
 template <int WD, int G>
 struct StageRegs { static constexpr int NIT = (G * WD + 31) / 32; double v[NIT]; };
 template <int WD, int G>
@@ -215,26 +192,7 @@ __device__ __forceinline__ void stage_out(double* __restrict__ g, const double* 
   }
 }
 
-// same for records scattered in global memory: record f lives at g + fid(f) * WD, fid held by lane f
-template <int WD, int STRIDE, int G>
-__device__ __forceinline__ void gather_in(const double* __restrict__ g, double* rows, int off, int ng, int lane, long long myfid) {
-  constexpr int NIT = (G * WD + 31) / 32;
-  double v[NIT];
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int idx = it * 32 + lane;
-    const bool ok = idx < ng * WD;
-    const int f = ok ? idx / WD : 0, i = idx - f * WD;
-    const long long fid = __shfl_sync(0xffffffffu, myfid, f);
-    v[it] = ok ? g[fid * WD + i] : 0.0;
-  }
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int idx = it * 32 + lane;
-    const int f = idx / WD, i = idx - f * WD;
-    if (idx < ng * WD) rows[f * STRIDE + off + i] = v[it];
-  }
-}
+// scattered counterpart of stage_out
 template <int WD, int STRIDE>
 __device__ __forceinline__ void scatter_out(double* __restrict__ g, const double* rows, int off, int ng, int lane, long long myfid) {
   for (int base = 0; base < ng * WD; base += 32) {
