@@ -338,7 +338,8 @@ def run_gpu(args):
                    "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_step": bytes_per_step(dim, edim, zdim[dom]), "algorithmic_bytes_per_launch": algo,
                    "traffic": traffic},
       "e2e": {"value": B * e2e_steps * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-              "steps": e2e_steps, "what": "HostStreamer.submit(t, kind, z_pinned_host, R_kind): H2D of z, fused step, D2H of x and y into pinned host memory EVERY step (3 streams overlap consecutive steps); P stays resident"},
+              "steps": e2e_steps, "d2h_GBps_per_gpu": d2h / (e2e_ms / e2e_steps * 1e-3) / 1e9, "h2d_GBps_per_gpu": h2d / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+              "what": "HostStreamer.submit(t, kind, z_pinned_host, R_kind): H2D of z, fused step, D2H of x and y into pinned host memory EVERY step (3 streams overlap consecutive steps); P stays resident; bound by the device-to-host link (d2h_GBps_per_gpu vs ~55-63 GB/s for PCIe Gen5 x16)"},
       "clocks": clocks.summary(),
     }
     if host_abi is not None:
