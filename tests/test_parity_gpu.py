@@ -555,3 +555,45 @@ def test_live_single_filter_dropin_path(gen_dir, oracle_dir):
       rg, rc = gpu.predict_and_observe(t, kind, data), cpu.predict_and_observe(t, kind, data)
       assert rg is not None and rc is not None
       assert rel_err(gpu.x, cpu.x) < TOL and rel_err(gpu.P, cpu.P) < TOL, (k, int(kind))   # contract: 1e-6
+
+
+def test_rewinding_scheduler_on_the_device(gen_dir, oracle_dir, monkeypatch):
+  """Late observations rewind and fast-forward per filter (rednose/helpers/ekf_sym.py:418-482) through the device ring
+  of RewindingScheduler; reference: one Python-driver instance per filter on the reference-generated CPU library.
+  (tests/test_scheduler_cpu.py runs the same stream bit-for-bit against the CPU oracle engine.)"""
+  import rednose_b200.ekf_sym as drv
+  from rednose_b200.filters.live import LiveKalman
+  from rednose_b200.scheduler import RewindingScheduler
+  depth = 32
+  monkeypatch.setattr(drv, "REWIND_TO_KEEP", depth)
+  B, zd = 5, {3: 1, 4: 3, 10: 3, 12: 3}
+  rng = np.random.default_rng(7)
+  x0 = np.tile(LiveKalman.initial_x, (B, 1)); x0[:, :3] += rng.normal(0, 10.0, (B, 3))
+  P0 = np.tile(np.diag(LiveKalman.initial_P_diag), (B, 1, 1))
+  Rk = {3: np.array([[0.2**2]]), 4: np.eye(3) * 0.025**2, 10: np.eye(3) * 0.5**2, 12: np.eye(3) * 25.0}
+  refs = [drv.EKF_sym(oracle_dir, "live", LiveKalman.Q, x0[b], P0[b], 23, 22, quaternion_idxs=[3], max_rewind_age=0.5) for b in range(B)]
+  e = _engine(gen_dir, "live", x0, P0, LiveKalman.Q, quaternion_idxs=[3], norm_after_predict=False)
+  s = RewindingScheduler(e, zd, depth=depth, max_rewind_age=0.5)
+  ref_dropped = 0
+  for tick in range(70):
+    now = 0.01 * (tick + 1)
+    ids, ts, ks, zs = [], [], [], {k: [] for k in zd}
+    for b in range(B):
+      if rng.random() < 0.25:
+        continue
+      u, tb = rng.random(), now + 1e-4 * b
+      if tick > 5 and u < 0.15:
+        tb -= rng.uniform(0.011, 0.06)
+      elif tick > 5 and u < 0.20:
+        tb -= 3.0
+      k = int(rng.choice([4, 10, 10, 4, 3 if tick > 12 else 4, 12]))
+      zb = {3: np.array([0.1]), 4: rng.normal(0, 0.01, 3), 10: rng.normal(0, 0.1, 3) + [0, 0, -9.8], 12: refs[b].state()[:3] + rng.normal(0, 1.0, 3)}[k]
+      ids.append(b); ts.append(tb); ks.append(k); zs[k].append(zb)
+      if refs[b].predict_and_update_batch(tb, k, zb[None], Rk[k][None]) is None:
+        ref_dropped += 1
+    if ids:
+      s.tick(np.array(ids), np.array(ts), np.array(ks), {k: np.array(v) for k, v in zs.items() if v}, Rk)
+  assert s.dropped == ref_dropped and s.rewinds > 10 and s.replayed > s.rewinds
+  for b in range(B):
+    assert rel_err(e.state()[b], refs[b].state()) < TOL and rel_err(e.covs()[b], refs[b].covs()) < TOL, b
+    assert int(s.cnt[b]) == len(refs[b].rewind_t) and abs(float(s.t_filter[b]) - refs[b].filter_time) < 1e-12
