@@ -83,8 +83,11 @@ typedef struct rednose_ekf_desc {
 
 /* ---- registry (librednose_b200.so; ekf_load.cc:4-39) ---- */
 void rednose_b200_register(const rednose_ekf_desc *desc);
-const rednose_ekf_desc *rednose_b200_lookup(const char *name);
-/* dlopen(<dir>/lib<name>.so) + ekf_get() + register; returns 0 on success */
+const rednose_ekf_desc *rednose_b200_lookup(const char *name);                 /* first registered plugin of that name (ekf_load.cc:13-20) */
+/* the plugin of that name loaded from that directory: unlike the reference's name-only table, two builds of one filter
+   (different directories) can be loaded side by side and a driver gets the one it asked for */
+const rednose_ekf_desc *rednose_b200_lookup_in(const char *directory, const char *name);
+/* dlopen(<dir>/lib<name>.so) + ekf_get() + register; idempotent per (directory, name) (ekf_load.cc:22-39); 0 on success */
 int rednose_b200_load_and_register(const char *directory, const char *name);
 
 /* ---- native single-filter driver (librednose_b200.so; rednose/helpers/ekf_sym.{h,cc} EKFSym) ----

@@ -26,8 +26,16 @@ namespace {
 
 constexpr size_t REWIND_TO_KEEP = 512;  // ekf_sym.h:18
 
-std::vector<const rednose_ekf_desc*>& registry() {
-  static std::vector<const rednose_ekf_desc*> v;
+// One entry per loaded plugin.  The reference keys its table by filter name only (ekf_load.cc:13-25: first match
+// wins, a second library of the same name is never loaded); here the directory a plugin was loaded from is kept as
+// well, so two builds of one filter (e.g. the CUDA library and a CPU build of the same model in a test process) can
+// coexist and a driver gets the one from the directory it asked for.
+struct Plugin {
+  const rednose_ekf_desc* desc;
+  std::string directory;   // empty: self-registered by its constructor, origin not (yet) known
+};
+std::vector<Plugin>& registry() {
+  static std::vector<Plugin> v;
   return v;
 }
 std::mutex& registry_mu() {
@@ -167,18 +175,28 @@ extern "C" {
 // ------------------------------------------------------------------ registry (ekf_load.cc) ---
 void rednose_b200_register(const rednose_ekf_desc* desc) {
   std::lock_guard<std::mutex> lk(registry_mu());
-  registry().push_back(desc);
+  for (const auto& p : registry())
+    if (p.desc == desc) return;
+  registry().push_back({desc, std::string()});
 }
 
 const rednose_ekf_desc* rednose_b200_lookup(const char* name) {
   std::lock_guard<std::mutex> lk(registry_mu());
-  for (const auto* d : registry())
-    if (std::strcmp(d->name, name) == 0) return d;  // first match wins (ekf_load.cc:13-20)
+  for (const auto& p : registry())
+    if (std::strcmp(p.desc->name, name) == 0) return p.desc;  // first match wins (ekf_load.cc:13-20)
+  return nullptr;
+}
+
+// the plugin `name` that was loaded from `directory` (nullptr if none)
+const rednose_ekf_desc* rednose_b200_lookup_in(const char* directory, const char* name) {
+  std::lock_guard<std::mutex> lk(registry_mu());
+  for (const auto& p : registry())
+    if (p.directory == directory && std::strcmp(p.desc->name, name) == 0) return p.desc;
   return nullptr;
 }
 
 int rednose_b200_load_and_register(const char* directory, const char* name) {
-  if (rednose_b200_lookup(name)) return 0;  // ekf_load.cc:23-25
+  if (rednose_b200_lookup_in(directory, name)) return 0;  // ekf_load.cc:23-25, per directory
   const std::string path = std::string(directory) + "/lib" + name + ".so";
   void* handle = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
   if (!handle) {
@@ -195,7 +213,13 @@ int rednose_b200_load_and_register(const char* directory, const char* name) {
     fprintf(stderr, "[rednose_b200] %s: ABI %d, runtime expects %d\n", path.c_str(), desc->abi_version, REDNOSE_B200_ABI_VERSION);
     return -3;
   }
-  if (!rednose_b200_lookup(name)) rednose_b200_register(desc);  // the library's constructor may already have done it
+  std::lock_guard<std::mutex> lk(registry_mu());
+  for (auto& p : registry())
+    if (p.desc == desc) {   // the library's constructor registered it already: record where it came from
+      if (p.directory.empty()) p.directory = directory;
+      return 0;
+    }
+  registry().push_back({desc, std::string(directory)});
   return 0;
 }
 
@@ -205,7 +229,8 @@ void* rednose_ekfsym_create(const char* directory, const char* name, const doubl
                             const int* maha_test_kinds, int n_maha, const int* quaternion_idxs, int n_quat, double max_rewind_age) {
   if (rednose_b200_load_and_register(directory, name) != 0) return nullptr;
   auto* e = new EKFSym();
-  e->ekf = rednose_b200_lookup(name);
+  e->ekf = rednose_b200_lookup_in(directory, name);
+  if (!e->ekf) e->ekf = rednose_b200_lookup(name);
   e->msckf = N > 0;
   e->N = N; e->dim_augment = dim_augment; e->dim_augment_err = dim_augment_err;
   e->dim_main = dim_main; e->dim_main_err = dim_main_err;

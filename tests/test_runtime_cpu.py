@@ -118,3 +118,28 @@ def test_python_maha_test_follows_the_reference_formula(oracle_dir):
     y = z[b] - h
     d = y @ np.linalg.inv(He @ P[b] @ He.T + R[b]) @ y
     assert kf.maha_test(xb, P[b], 4, z[b], R[b]) == bool(d <= chi2_ppf(0.95, 3))
+
+
+def test_two_builds_of_one_filter_coexist_per_directory(oracle_dir, tmp_path):
+  """The reference's registry is keyed by name (ekf_load.cc:13-25: the second library of a name is never loaded);
+  here a plugin is found by (directory, name), so a driver created on directory B runs B's library even when a
+  filter of the same name from directory A is already loaded (CUDA library next to a CPU build in one process)."""
+  import ctypes
+  import shutil
+  rt = runtime()
+  rt.rednose_b200_lookup_in.restype = ctypes.c_void_p
+  rt.rednose_b200_lookup_in.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+  other = str(tmp_path)
+  for f in ("libkinematic.so", "kinematic.h"):
+    shutil.copy(f"{oracle_dir}/{f}", f"{other}/{f}")
+  assert rt.rednose_b200_load_and_register(oracle_dir.encode(), b"kinematic") == 0
+  assert rt.rednose_b200_load_and_register(other.encode(), b"kinematic") == 0
+  a, b = rt.rednose_b200_lookup_in(oracle_dir.encode(), b"kinematic"), rt.rednose_b200_lookup_in(other.encode(), b"kinematic")
+  assert a and b and a != b                                       # two distinct plugin descriptors
+  assert rt.rednose_b200_lookup(b"kinematic") in (a, b)            # name-only lookup: first registered
+  assert not rt.rednose_b200_lookup_in(b"/nonexistent", b"kinematic")
+  Q, x0, P0 = np.diag([0.01, 4.0]), np.array([0.5, 0.0]), np.eye(2)
+  k1, k2 = EKF_sym_pyx(oracle_dir, "kinematic", Q, x0, P0, 2, 2), EKF_sym_pyx(other, "kinematic", Q, x0, P0, 2, 2)
+  for kf in (k1, k2):
+    kf.predict_and_update_batch(0.1, 1, np.array([[1.2]]), np.array([[[0.01]]]))
+  assert np.array_equal(k1.state(), k2.state())
