@@ -56,6 +56,15 @@ struct HostCtx {
 
 constexpr int THREAD_MAX_EDIM = 6;
 
+// true exactly once per kernel address (kernels of one signature share a pointer type, so the key is the address):
+// the caller then sets the kernel's shared-memory attributes.  Entry points may be called from several host threads.
+inline bool first_launch_of(const void* kern) {
+  static std::mutex mu;
+  static std::unordered_set<const void*> configured;
+  std::lock_guard<std::mutex> lk(mu);
+  return configured.insert(kern).second;
+}
+
 template <class M, class K, bool PRED, bool UPD>
 inline void launch_step(const StepArgs<M::NG>& a, cudaStream_t st) {
   if (a.B <= 0) return;
@@ -81,8 +90,7 @@ inline void launch_step(const StepArgs<M::NG>& a, cudaStream_t st) {
       constexpr size_t smem = pair_smem_bytes<M, K, G>();
       const unsigned grid = (unsigned)((a.B + G - 1) / G);
       auto run = [&](void (*kern)(const StepArgs<M::NG>)) {
-        static std::unordered_set<const void*> configured;
-        if (configured.insert((const void*)kern).second) {
+        if (first_launch_of((const void*)kern)) {
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
@@ -106,8 +114,7 @@ inline void launch_step(const StepArgs<M::NG>& a, cudaStream_t st) {
       const long long per_cta = (long long)G * W;
       const unsigned grid = (unsigned)((a.B + per_cta - 1) / per_cta);
       auto run = [&](void (*kern)(const StepArgs<M::NG>)) {
-        static std::unordered_set<const void*> configured;  // kernels share one pointer type: key by address
-        if (configured.insert((const void*)kern).second) {
+        if (first_launch_of((const void*)kern)) {
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
