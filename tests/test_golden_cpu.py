@@ -39,3 +39,33 @@ def test_restated_rts_matches_reference_rts(oracle_dir, gold):
   for b in range(2):
     xs, Ps = rts_smooth(o, gold[f"x_pred{b}"], gold[f"x_filt{b}"], gold[f"P_pred{b}"], gold[f"P_filt{b}"], gold["t"], 23, 22, norm_quats=True)
     assert rel_err(xs, gold[f"xs{b}"]) < 1e-12 and rel_err(Ps, gold[f"Ps{b}"]) < 1e-12
+
+
+def _msckf_gold():
+  return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "msckf_reference.npz"))
+
+
+def test_oracle_matches_reference_python_maths_on_msckf(oracle_dir):
+  """MSCKF pieces: block predict, feature update through the left-null-space projection (reference numpy: SVD null(),
+  oracle: restated fullPivLu().kernel(), ekf_c.c:66-76) with the Mahalanobis gate armed, augment.  x and P are
+  basis-invariant and must agree at every step (tests/golden/make_golden_msckf.py)."""
+  if not os.path.exists(os.path.join(oracle_dir, "libmsckf.so")):
+    pytest.skip("oracle/_ref/libmsckf.so not built")
+  from rednose_b200.ekf_sym import EKF_sym
+  from rednose_b200.filters.live import DIM_STATE, DIM_STATE_ERR
+  from rednose_b200.filters.msckf import DIM_AUGMENT, DIM_AUGMENT_ERR, N_CLONES, MsckfKalman
+  g = _msckf_gold()
+  feat = int(MsckfKalman.feature_kind)
+  quats = [3] + [DIM_STATE + 3 + 7 * c for c in range(N_CLONES)]
+  for b in range(2):
+    kf = EKF_sym(oracle_dir, "msckf", g["Q"], g["x0"][b], g["P0"][b], DIM_STATE, DIM_STATE_ERR, N=N_CLONES, dim_augment=DIM_AUGMENT,
+                 dim_augment_err=DIM_AUGMENT_ERR, maha_test_kinds=[feat], quaternion_idxs=quats)
+    for k, kind in enumerate(g["kinds"]):
+      kind = int(kind)
+      m = 2 * N_CLONES if kind == feat else 3
+      z, R = g[f"z{b}"][k, :m], np.diag(g[f"Rdiag{b}"][k, :m])
+      r = kf.predict_and_update_batch(float(g["t"][k]), kind, z[None], R[None], extra_args=[g["point"][b]] if kind == feat else [[]],
+                                      augment=bool(g["augment"][k]))
+      assert r is not None
+      ex, eP = rel_err(kf.state(), g[f"xk{b}"][k]), rel_err(kf.covs(), g[f"Pk{b}"][k])
+      assert ex < 1e-10 and eP < 1e-8, (b, k, kind, ex, eP)
