@@ -5,7 +5,7 @@ the quantile is a *linear interpolation* over the probability grid 0.01 .. 0.98
 (step 0.01) of exact chi2 quantiles, not the exact ppf.  The reference ships the
 grid as a 200x98 .npy table; here each row is recomputed on demand with scipy
 and memoised, which yields the same float64 values (checked in
-tests/test_support.py against the 0.95 constants listed in SURVEY.md App. B).
+tests/test_support_cpu.py against the reference's shipped table).
 """
 from functools import lru_cache
 

@@ -3,8 +3,9 @@ rednose/helpers/sympy_helpers.py:1-120; live_kf.py:9 uses euler_rotate,
 quat_matrix_r, quat_rotate).  Symbolic builders return sympy matrices, numeric
 ones numpy arrays.  Conventions (kept identical to the reference so generated
 models agree): quaternions are [w, x, y, z]; eulers are (roll, pitch, yaw) with
-R = Rz(yaw) Ry(pitch) Rx(roll); quat_rotate returns the TRANSPOSE of the
-body->world matrix built from the Hamilton products.
+R = Rz(yaw) Ry(pitch) Rx(roll); the symbolic quat_rotate(q) and the numeric
+quat2rot(q) are the same matrix (tests/test_support_cpu.py, which also checks the
+symbolic builders against the reference's own helpers where it is mounted).
 """
 import numpy as np
 import sympy as sp
