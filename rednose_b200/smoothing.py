@@ -38,10 +38,14 @@ class TiledSmoother:
     per = history_bytes_per_filter(self.dim_x, self.dim_err, T) + 8 * (self.dim_err**2 + self.dim_x)
     return max(1, int(self.budget // per))
 
-  def run(self, x0, P0, T, obs_fn, sink, norm_quats=False, t0=0.0):
+  def run(self, x0, P0, T, obs_fn, sink, norm_quats=False, t0=0.0, passes=1):
     """x0 [B, DIM], P0 [B, EDIM, EDIM] (host or device).  obs_fn(k, lo, hi) -> (t, kind, z [hi-lo, m], R) gives the
     observation of step k for filters lo..hi.  sink(lo, hi, xs [T, n, DIM], Ps [T, n, EDIM, EDIM]) receives device
-    views that are only valid during the call.  Returns the number of tiles."""
+    views that are only valid during the call.  Returns the number of tiles.
+
+    passes > 1: "multiple forward and backwards passes of the data" (reference README.md:41-45) -- each further pass
+    restarts the forward filter of the tile from the previous pass's smoothed estimate at the first step
+    (x_{0|N}, P_{0|N}), which removes the dependence on a poor initialisation; the sink sees the last pass."""
     B = x0.shape[0]
     n_tile = min(self.tile_size(T), B)
     tiles = 0
@@ -54,12 +58,15 @@ class TiledSmoother:
       else:
         self._engine.init_state(x0[lo:hi], P0[lo:hi], None)
       eng, hist = self._engine, self._hist
-      hist.n = 0
-      eng.filter_time = t0
-      for k in range(T):
-        t, kind, z, R = obs_fn(k, lo, hi)
-        eng.step_recorded(hist, kind, t, z, R)
-      xs, Ps = eng.rts_smooth(hist, norm_quats=norm_quats, quaternion_idxs=self.quat or (3,), in_place=True)
+      for p in range(max(1, int(passes))):
+        if p > 0:   # the smoothed slabs alias the history buffers the next forward pass overwrites: copy step 0 out first
+          eng.init_state(xs[0].clone(), Ps[0].clone(), None)
+        hist.n = 0
+        eng.filter_time = t0
+        for k in range(T):
+          t, kind, z, R = obs_fn(k, lo, hi)
+          eng.step_recorded(hist, kind, t, z, R)
+        xs, Ps = eng.rts_smooth(hist, norm_quats=norm_quats, quaternion_idxs=self.quat or (3,), in_place=True)
       sink(lo, hi, xs, Ps)
       tiles += 1
     return tiles
