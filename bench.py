@@ -532,44 +532,94 @@ def run_extras(dev, peak):
 
 
 # ------------------------------------------------------------------- reference arm / CPU baseline ---
-def cpu_reference(fname, workload, budget_s=15.0, steps=None):
-  """The reference's C path (oracle/_ref: reference-generated leaf C + Eigen-free restatement of ekf_c.c, g++ -O2)
-  looping predict + update_<kind> per filter on all host cores, on a bounded sample of the same workload."""
-  from oracle import build_ref
-  from oracle.handle import Oracle
-  if build_ref.reference_available():
-    build_ref.build(fname)
-  o = Oracle(build_ref.OUT, fname)
-  cores = os.cpu_count() or 1
-  Bs = 4096
-  x, P, Q, pools, (dim, edim), quat = _cpu_problem(fname, Bs)
-  sched = kind_schedule(fname, 1000)
-  # calibrate, then size the sample for ~budget_s of CPU work
+CPU_WHAT = ("reference-generated leaf C (rednose gen_code, unmodified) + Eigen-free restatement of ekf_c.c, g++ -O2 -g -fPIC (SConstruct:25-38); "
+            "per filter the call order of ekf_sym.cc:206-213; state resident in one arena first-touched and stepped IN PLACE by a pool of "
+            "pinned worker threads (oracle/batch_runner.inc), no per-step array copies")
+
+
+class CpuArm:
+  """The reference's C path (oracle/_ref) on the host cores over a resident batch of filters, stepped in place."""
+
+  def __init__(self, fname, B, nthreads=None, seed=99):
+    from oracle import build_ref
+    from oracle.handle import Arena, Oracle
+    if build_ref.reference_available():
+      build_ref.build(fname)
+    self.fname, self.B = fname, B
+    self.o = Oracle(build_ref.OUT, fname)
+    x, P, self.Q, self.pools, (self.dim, self.edim), self.quat = _cpu_problem(fname, B, seed)
+    self.Q = np.ascontiguousarray(self.Q, dtype=np.float64)
+    self.arena = Arena(self.o, B, nthreads=nthreads)
+    self.arena.load(x, P)             # P [EDIM, EDIM] is broadcast; pages are first-touched by the workers
+    self.sched = kind_schedule(fname, 4096)
+    self.it = 0
+
+  def step(self):
+    k = self.sched[self.it % len(self.sched)]
+    zp, R = self.pools[k]
+    self.arena.step(k, self.Q, 0.01, zp[self.it % zp.shape[0]], R, quat_idxs=self.quat, flags=3)
+    self.it += 1
+
+  def finite(self):
+    n = min(self.B, 4096)
+    x, P = self.arena.read(0, n)
+    return bool(np.isfinite(x).all() and np.isfinite(P).all())
+
+  def close(self):
+    self.arena.close()
+
+
+def _threads():
+  try:
+    return len(os.sched_getaffinity(0))
+  except AttributeError:
+    return os.cpu_count() or 1
+
+
+def _calibrate(fname, nthreads, n=4096):
+  """seconds per filter-step with `nthreads` workers (small resident sample, warm)."""
+  arm = CpuArm(fname, n * max(1, nthreads // 4), nthreads=nthreads)
+  arm.step()
   t = time.perf_counter()
-  k = sched[1]
-  o.batch_step(k, x, P, Q, 0.01, pools[k][0][0], pools[k][1], quat_idxs=quat, flags=3, nthreads=cores)
-  per_filter_step = (time.perf_counter() - t) / Bs
+  for _ in range(3):
+    arm.step()
+  per = (time.perf_counter() - t) / 3 / arm.B
+  arm.close()
+  return max(per, 1e-10)
+
+
+def cpu_reference(fname, workload, budget_s=15.0, steps=None, full_batch=None):
+  """cpu_baseline of the GPU line: the reference's C path on all host cores over a bounded resident sample of the
+  same workload (same kind schedule), plus one-thread and per-filter-Python-driver figures for context."""
+  cores = _threads()
   n_steps = steps or 20
-  Bs = int(max(1024, min(200_000, budget_s / (per_filter_step * n_steps))))
-  x, P, Q, pools, (dim, edim), quat = _cpu_problem(fname, Bs)
+  per = _calibrate(fname, cores)
+  full = full_batch or WORKLOADS[workload]["batch"]
+  Bs = int(max(1024, min(full, budget_s / (per * (n_steps + 2)))))
+  arm = CpuArm(fname, Bs, nthreads=cores)
+  arm.step(); arm.step()
   t = time.perf_counter()
-  for i in range(n_steps):
-    k = sched[i]
-    zp, R = pools[k]
-    x, P, _ = o.batch_step(k, x, P, Q, 0.01, zp[i % zp.shape[0]], R, quat_idxs=quat, flags=3, nthreads=cores)
+  for _ in range(n_steps):
+    arm.step()
   el = time.perf_counter() - t
-  assert np.isfinite(x).all()
-  # context numbers (SURVEY.md section 8d): one thread, and the per-filter Python driving pattern the reference ships
-  n1 = min(Bs, 4000)
+  assert arm.finite()
+  pinned = arm.arena.pinned
+  arm.close()
+  n1 = 4096
+  one = CpuArm(fname, n1, nthreads=1)
+  one.step()
   t1 = time.perf_counter()
-  o.batch_step(sched[1], x[:n1], P[:n1], Q, 0.01, pools[sched[1]][0][0][:n1], pools[sched[1]][1][:n1], quat_idxs=quat, flags=3, nthreads=1)
-  one_thread = n1 / (time.perf_counter() - t1)
+  for _ in range(3):
+    one.step()
+  one_thread = 3 * n1 / (time.perf_counter() - t1)
   py_driver = None
   try:
+    from oracle import build_ref
     from rednose_b200.ekf_sym import EKF_sym
-    kf = EKF_sym(build_ref.OUT, fname, Q, x[0], P[0], dim, edim, quaternion_idxs=quat)   # Python driver on the CPU oracle library
-    k = sched[1]
-    zp, R = pools[k]
+    x, P = one.arena.read(0, 1)
+    kf = EKF_sym(build_ref.OUT, fname, one.Q, x[0], P[0], one.dim, one.edim, quaternion_idxs=one.quat)   # Python driver on the CPU oracle library
+    k = one.sched[1]
+    zp, R = one.pools[k]
     tt, n_calls = 0.0, 300
     t2 = time.perf_counter()
     for i in range(n_calls):
@@ -578,19 +628,23 @@ def cpu_reference(fname, workload, budget_s=15.0, steps=None):
     py_driver = n_calls / (time.perf_counter() - t2)
   except Exception:  # pylint: disable=broad-except
     pass
-  return {"value": Bs * n_steps / el, "unit": "steps/s", "cores": cores, "kind": "port",
-          "one_thread_steps_per_s": one_thread, "python_driver_per_filter_steps_per_s": py_driver,
-          "sample": f"{Bs} {fname} filters x {n_steps} steps of workload {workload} (same kind schedule), {el:.1f} s",
-          "what": "reference-generated leaf C (rednose gen_code, unmodified) + Eigen-free restatement of ekf_c.c, g++ -O2, threads over filters"}
+  one.close()
+  v = Bs * n_steps / el
+  return {"value": v, "unit": "steps/s", "cores": cores, "threads": cores, "threads_pinned": pinned, "kind": "port",
+          "one_thread_steps_per_s": one_thread, "thread_scaling_efficiency": v / (cores * one_thread), "copy_bytes_per_step": 0,
+          "python_driver_per_filter_steps_per_s": py_driver,
+          "sample": f"{Bs} {fname} filters resident x {n_steps} in-place steps of workload {workload} (same kind schedule), {el:.1f} s",
+          "same_batch_as_gpu_arm": Bs == full, "what": CPU_WHAT}
 
 
-def _cpu_problem(fname, B):
-  # the oracle arm must not touch the CUDA libraries: build the same synthetic problem with the oracle's own h_k
-  rng = np.random.default_rng(99)
+def _cpu_problem(fname, B, seed=99):
+  # the oracle arm must not touch the CUDA libraries: build the same synthetic problem with the oracle's own h_k.
+  # P is ONE [EDIM, EDIM] matrix (broadcast by the arena, as the GPU arm broadcasts it on the device); R is per filter.
+  rng = np.random.default_rng(seed)
   if fname == "kinematic":
     from rednose_b200.filters.kinematic import KinematicKalman as F
     x = np.tile(F.initial_x, (B, 1)) + rng.normal(size=(B, 2))
-    P = np.tile(np.diag(F.initial_P_diag), (B, 1, 1))
+    P = np.diag(F.initial_P_diag).astype(np.float64)
     return x, P, F.Q.copy(), {1: (rng.normal(0.0, 0.1, (4, B, 1)), np.tile(np.array([[0.1**2]]), (B, 1, 1)))}, (2, 2), []
   from oracle import build_ref
   from rednose_b200.filters.live import LiveKalman as F
@@ -602,8 +656,10 @@ def _cpu_problem(fname, B):
   x = np.tile(x_true, (B, 1))
   x[:, 0:3] += rng.normal(0, 10.0, (B, 3))
   x[:, 7:10] += rng.normal(0, 1.0, (B, 3))
+  x[:, 10:13] += rng.normal(0, 0.05, (B, 3))
+  x[:, 17:20] += rng.normal(0, 0.3, (B, 3))
   pdiag = np.array([25.0] * 3 + [0.05**2] * 3 + [1.0] * 3 + [0.1**2] * 3 + [0.01**2] * 3 + [0.01**2] + [0.5**2] * 3 + [0.01**2] * 3)
-  P = np.tile(np.diag(pdiag), (B, 1, 1))
+  P = np.diag(pdiag)
   pools = {}
   for k, rdiag in LIVE_R.items():
     hz = np.zeros(3)
@@ -613,51 +669,46 @@ def _cpu_problem(fname, B):
 
 
 def run_reference(args):
-  """Reference arm: the reference's C path (oracle/_ref) on the host cores, same workload / metric / unit.
-  The synthetic problem is built once; every step is one bounded pass (a few predict+update sub-steps of the
-  workload's kind schedule over a fixed sample of filters) sized so that warm-up + K steps take about two minutes."""
+  """Reference arm: the reference's C path (oracle/_ref) on ALL host cores, same workload / metric / unit as the GPU arm.
+  One step = one in-place pass of predict + update_<kind> (the workload's kind schedule) over the resident batch: the
+  workload's full batch when warm-up + K steps fit in ~150 s on this box's cores, else the largest sample that does."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  from oracle import build_ref
-  from oracle.handle import Oracle
   wl = WORKLOADS[args.workload]
-  fname = wl["filter"]
-  dim, edim = (2, 2) if fname == "kinematic" else (23, 22)
-  if build_ref.reference_available():
-    build_ref.build(fname)
-  o = Oracle(build_ref.OUT, fname)
-  cores = os.cpu_count() or 1
-  sched = kind_schedule(fname, 4096)
-  # calibrate on a small sample
-  x, P, Q, pools, _, quat = _cpu_problem(fname, 2048)
-  t = time.perf_counter()
-  k = sched[1]
-  o.batch_step(k, x, P, Q, 0.01, pools[k][0][0], pools[k][1], quat_idxs=quat, flags=3, nthreads=cores)
-  per = max((time.perf_counter() - t) / 2048, 1e-9)
-  n_sub = 4
-  total_budget = 110.0
-  Bs = int(max(cores * 8, min(400_000, total_budget / (args.steps + args.warmup) / (per * n_sub))))
-  x, P, Q, pools, _, quat = _cpu_problem(fname, Bs)
-  times, it = [], 0
+  fname, full = wl["filter"], (args.batch or wl["batch"])
+  cores = _threads()
+  per = _calibrate(fname, cores)
+  total_budget = 150.0
+  Bs = int(max(cores * 8, min(full, total_budget / (args.steps + args.warmup) / per)))
+  arm = CpuArm(fname, Bs, nthreads=cores)
+  times = []
   for i in range(args.warmup + args.steps):
     t = time.perf_counter()
-    for _ in range(n_sub):
-      k = sched[it]
-      zp, R = pools[k]
-      x, P, _y = o.batch_step(k, x, P, Q, 0.01, zp[it % zp.shape[0]], R, quat_idxs=quat, flags=3, nthreads=cores)
-      it += 1
+    arm.step()
     if i >= args.warmup:
       times.append(time.perf_counter() - t)
-  assert np.isfinite(x).all()
-  v = Bs * n_sub / float(np.mean(times))
-  cb = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-        "sample": f"{Bs} {fname} filters x {n_sub} sub-steps per step, {args.steps} timed steps, workload {args.workload} kind schedule",
-        "what": "reference-generated leaf C (rednose gen_code, unmodified) + Eigen-free restatement of ekf_c.c, g++ -O2, threads over filters"}
+  assert arm.finite()
+  pinned, resident = arm.arena.pinned, arm.arena.bytes_resident
+  arm.close()
+  one = CpuArm(fname, 4096, nthreads=1)
+  one.step()
+  t1 = time.perf_counter()
+  for _ in range(3):
+    one.step()
+  one_thread = 3 * 4096 / (time.perf_counter() - t1)
+  one.close()
+  v = Bs / float(np.mean(times))
+  cb = {"value": v, "unit": "steps/s", "cores": cores, "threads": cores, "threads_pinned": pinned, "kind": "port",
+        "one_thread_steps_per_s": one_thread, "thread_scaling_efficiency": v / (cores * one_thread), "copy_bytes_per_step": 0,
+        "resident_bytes": resident,
+        "sample": f"{Bs} {fname} filters resident ({'the full workload batch' if Bs == full else f'of {full}'}), one in-place pass per step, {args.steps} timed steps, workload {args.workload} kind schedule",
+        "what": CPU_WHAT}
   line = {"impl": "reference", "metric": "fused EKF predict+update steps/s (batched, float64)", "value": v, "unit": "steps/s",
           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True,
           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-          "config": {"workload": args.workload, "filter": fname, "dim": dim, "edim": edim, "sample_filters": Bs},
+          "config": {"workload": args.workload, "filter": fname, "filters_per_gpu": Bs, "dim": arm.dim, "edim": arm.edim, "sample_filters": Bs,
+                     "same_batch_as_gpu_arm": Bs == full},
           "cpu_baseline": cb,
           "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
   print(json.dumps(line))

@@ -100,7 +100,8 @@ def assemble(name, gen_dir):
           f"  {name}_f_fun, {name}_F_fun, {name}_err_fun, {name}_inv_err_fun, {name}_H_mod_fun, {name}_predict, ohs_, oHs_, oHes_, oupd_,",
           "  0, onone_, osets_, 0, onone_, oext_, nullptr, nullptr, nullptr, nullptr, nullptr };",
           "}", 'extern "C" void* ekf_get() { return (void*)&odesc_; }', ""]
-  runner = runner.replace("@NAME@", name).replace("@DISPATCH@", dispatch) + "\n".join(desc)
+  dispatch_arena = "\n".join(f"          case {k}: {name}_update_{k}(xb, Pb, z, R, ea); break;" for k in kinds)
+  runner = runner.replace("@DISPATCH_ARENA@", dispatch_arena).replace("@NAME@", name).replace("@DISPATCH@", dispatch) + "\n".join(desc)
   tu = (f"// assembled by oracle/build_ref.py from the reference generator's output -- not committed\n"
         f"#include <math.h>\n#include <string.h>\n#include <stddef.h>\n#include <vector>\n#include <thread>\n#include <cmath>\n{head}\n"
         f"#include \"{os.path.join(HERE, 'ekf_oracle_core.h')}\"\n{post}\n{runner}\n")
@@ -128,7 +129,14 @@ def build(name, model_spec=None, force=False):
   with open(os.path.join(gen_dir, f"{name}.h"), encoding="utf-8") as f:
     hdr = f.read()
   hdr += (f"\nvoid {name}_oracle_batch_step(int kind, double *x, double *P, double *Q, const double *dt_arr, double dt, "
-          f"double *z, double *R, double *ea, int zdim, int eadim, long long B, int nthreads, const int *quat_idxs, int n_quat, int flags);\n")
+          f"double *z, double *R, double *ea, int zdim, int eadim, long long B, int nthreads, const int *quat_idxs, int n_quat, int flags);\n"
+          f"void *{name}_oracle_arena_create(long long B, int nthreads, int pin);\n"
+          f"void {name}_oracle_arena_destroy(void *h);\n"
+          f"void {name}_oracle_arena_info(void *h, long long *out);\n"
+          f"void {name}_oracle_arena_load(void *h, const double *x, long long x_stride, const double *P, long long P_stride);\n"
+          f"void {name}_oracle_arena_step(void *h, int kind, const double *Q, const double *dt_arr, double dt, const double *z, double *y, "
+          f"const double *R, long long R_stride, const double *ea, int zdim, int eadim, const int *quat_idxs, int n_quat, int flags);\n"
+          f"void {name}_oracle_arena_read(void *h, long long b0, long long b1, double *x, double *P);\n")
   with open(os.path.join(OUT, f"{name}.h"), "w", encoding="utf-8") as f:
     f.write(hdr)
   return lib
