@@ -142,6 +142,48 @@ def build(name, model_spec=None, force=False):
   return lib
 
 
+def build_features(K=10, force=False):
+  """oracle/_ref/libfeatures_<K>.so: oracle/features_oracle.h around res_fun / jac_fun printed by the reference's own
+  sympy_into_c (run from /root/reference in a subprocess) from rednose_b200.features.residual_sym(K)."""
+  name = f"features_{K}"
+  lib = os.path.join(OUT, f"lib{name}.so")
+  core = os.path.join(HERE, "features_oracle.h")
+  if not force and os.path.exists(lib) and all(os.path.getmtime(p) <= os.path.getmtime(lib) for p in (core, __file__)):
+    return lib
+  if not reference_available():
+    raise RuntimeError(f"{REF} not present: oracle/_ref can only be (re)built where the reference is mounted")
+  gen_dir = os.path.join(OUT, "gen")
+  os.makedirs(gen_dir, exist_ok=True)
+  env = dict(os.environ, PYTHONPATH=REF + os.pathsep + REPO)
+  leaf = os.path.join(gen_dir, f"{name}_leaf.c")
+  code = textwrap.dedent(f"""
+    import os, rednose
+    assert os.path.realpath(rednose.__file__).startswith(os.path.realpath({REF!r})), rednose.__file__
+    from rednose.helpers.sympy_helpers import sympy_into_c      # the reference's printer, unmodified
+    from rednose_b200.features import residual_sym
+    res, jac, args = residual_sym({K})
+    header, code = sympy_into_c([('res_fun', res, args), ('jac_fun', jac, args)])
+    open({leaf!r}, 'w').write(code)
+  """)
+  subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd="/tmp")
+  with open(leaf, encoding="utf-8") as f:
+    leaf_c = f.read()
+  tu = (f"// assembled by oracle/build_ref.py -- not committed\n#include <math.h>\n#include <string.h>\n#define KDIM {K}\n#define K {K}\n"
+        f"extern \"C\" {{\n{leaf_c}\n}}\n#include \"{core}\"\n")
+  path = os.path.join(gen_dir, f"{name}_oracle.cpp")
+  with open(path, "w", encoding="utf-8") as f:
+    f.write(tu)
+  subprocess.run(["g++", "-O2", "-g", "-fPIC", "-std=c++17", "-shared", "-o", lib, path], check=True)
+  with open(os.path.join(OUT, f"{name}.h"), "w", encoding="utf-8") as f:
+    f.write("void compute_pos(double *to_c, double *poses, double *img_positions, double *param, double *pos);\n"
+            "void res_fun(double *abr, double *poses, double *img_positions, double *out);\n"
+            "void jac_fun(double *abr, double *poses, double *img_positions, double *out);\n"
+            "void merge_features(double *tracks, double *features, long long *empty_idxs);\n"
+            "void merge_features_n(double *tracks, double *features, long long *empty_idxs, int n_features, int n_tracks);\n"
+            "int sane(double *track);\n")
+  return lib
+
+
 if __name__ == "__main__":
   names = sys.argv[1:] or ["kinematic", "live", "compare"]
   for n in names:
