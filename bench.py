@@ -569,11 +569,44 @@ class CpuArm:
     self.arena.close()
 
 
-def _threads():
+def _cpu_limits():
+  """(logical CPUs this process may run on, cgroup CPU quota in CPUs or None).  The GPU boxes of this pool run the
+  container under a CFS quota (cpu.max) far below the 128 logical CPUs the affinity mask shows; threads beyond the quota
+  are throttled, not run (measured: linear to the quota, then flat, then worse -- profiles/r02_cpu_thread_sweep.txt)."""
   try:
-    return len(os.sched_getaffinity(0))
+    n = len(os.sched_getaffinity(0))
   except AttributeError:
-    return os.cpu_count() or 1
+    n = os.cpu_count() or 1
+  quota = None
+  try:
+    with open("/sys/fs/cgroup/cpu.max", encoding="utf-8") as f:       # cgroup v2: "<quota> <period>" or "max <period>"
+      q, per = f.read().split()[:2]
+      if q != "max":
+        quota = float(q) / float(per)
+  except (OSError, ValueError):
+    try:
+      with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", encoding="utf-8") as f:   # cgroup v1
+        q = float(f.read())
+      with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us", encoding="utf-8") as f:
+        per = float(f.read())
+      if q > 0:
+        quota = q / per
+    except (OSError, ValueError):
+      pass
+  return n, quota
+
+
+def _threads():
+  """host threads the reference arm uses: every CPU it can actually get (affinity mask capped by the cgroup quota)."""
+  n, quota = _cpu_limits()
+  if quota is not None:
+    n = max(1, min(n, int(quota + 0.5)))
+  return n
+
+
+def _cpu_info():
+  n, quota = _cpu_limits()
+  return {"logical_cpus": n, "cgroup_cpu_quota": quota}
 
 
 def _calibrate(fname, nthreads, n=4096):
@@ -630,7 +663,7 @@ def cpu_reference(fname, workload, budget_s=15.0, steps=None, full_batch=None):
     pass
   one.close()
   v = Bs * n_steps / el
-  return {"value": v, "unit": "steps/s", "cores": cores, "threads": cores, "threads_pinned": pinned, "kind": "port",
+  return {"value": v, "unit": "steps/s", "cores": cores, "threads": cores, "threads_pinned": pinned, "kind": "port", **_cpu_info(),
           "one_thread_steps_per_s": one_thread, "thread_scaling_efficiency": v / (cores * one_thread), "copy_bytes_per_step": 0,
           "python_driver_per_filter_steps_per_s": py_driver,
           "sample": f"{Bs} {fname} filters resident x {n_steps} in-place steps of workload {workload} (same kind schedule), {el:.1f} s",
@@ -699,7 +732,7 @@ def run_reference(args):
   one_thread = 3 * 4096 / (time.perf_counter() - t1)
   one.close()
   v = Bs / float(np.mean(times))
-  cb = {"value": v, "unit": "steps/s", "cores": cores, "threads": cores, "threads_pinned": pinned, "kind": "port",
+  cb = {"value": v, "unit": "steps/s", "cores": cores, "threads": cores, "threads_pinned": pinned, "kind": "port", **_cpu_info(),
         "one_thread_steps_per_s": one_thread, "thread_scaling_efficiency": v / (cores * one_thread), "copy_bytes_per_step": 0,
         "resident_bytes": resident,
         "sample": f"{Bs} {fname} filters resident ({'the full workload batch' if Bs == full else f'of {full}'}), one in-place pass per step, {args.steps} timed steps, workload {args.workload} kind schedule",

@@ -56,22 +56,15 @@ struct HostCtx {
 
 constexpr int THREAD_MAX_EDIM = 6;
 
-// true exactly once per kernel address (kernels of one signature share a pointer type, so the key is the address):
-// the caller then sets the kernel's shared-memory attributes.  Entry points may be called from several host threads.
-inline bool first_launch_of(const void* kern) {
-  static std::mutex mu;
-  static std::unordered_set<const void*> configured;
-  std::lock_guard<std::mutex> lk(mu);
-  return configured.insert(kern).second;
-}
-
 template <class M, class K, bool PRED, bool UPD>
 inline void launch_step(const StepArgs<M::NG>& a, cudaStream_t st) {
   if (a.B <= 0) return;
-  if constexpr (M::EDIM <= THREAD_MAX_EDIM) {
+  // feature-track kinds (left-null-space projection with He, ekf_c.c:66-76) exist only in the CTA kernel: they go there
+  // whatever the state size
+  if constexpr (M::EDIM <= THREAD_MAX_EDIM && !K::HAS_HE) {
     const unsigned grid = (unsigned)((a.B + 127) / 128);
     ekf_step_thread<M, K, PRED, UPD><<<grid, 128, 0, st>>>(a);
-  } else if constexpr (M::EDIM <= 32) {
+  } else if constexpr (M::EDIM <= 32 && !K::HAS_HE) {
     if (use_tma<M>() && (reinterpret_cast<uintptr_t>(a.P) & 15u)) {
       fprintf(stderr, "[rednose_b200] P must be 16-byte aligned (bulk-copy staging of covariance tiles)\n");
       last_status() = (int)cudaErrorMisalignedAddress;

@@ -8,6 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace rnb {
 
@@ -168,6 +171,18 @@ inline bool check(cudaError_t e, const char* what) {
   fprintf(stderr, "[rednose_b200] CUDA failure in %s: %s\n", what, cudaGetErrorString(e));
   if (getenv("REDNOSE_B200_ABORT_ON_ERROR")) abort();
   return false;
+}
+
+
+// true exactly once per (device, kernel address): the caller then sets the kernel's shared-memory attributes, which
+// are per device.  Entry points may be called from several host threads and for several devices in one process.
+inline bool first_launch_of(const void* kern) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> configured;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  return configured.insert({dev, kern}).second;
 }
 
 }  // namespace rnb

@@ -127,19 +127,28 @@ __global__ void __launch_bounds__(64) ekf_leaf_thread(const StepArgs<M::NG> a, i
 }
 
 // ------------------------------------------------------------------ CTA kernel ---
+// Shared-memory plan of one CTA (= one filter), 3 warps, thread j <-> column j of the covariance:
+//   Ppk   the symmetric covariance, PACKED lower-triangular row-major (E (E + 1) / 2 doubles: 27.2 kB at EDIM 82 instead
+//         of 53.8 kB) -- this is what lets 4 CTAs share an SM instead of 2, so that the serial sections of one filter
+//         (the small factorisation, the projections) overlap the wide sections of three others;
+//   U     [column][k]: first H_err P (unprojected, for S), later U = L^-1 (A^T H_err P) of S = L D L^T; the rank-m
+//         covariance update is P -= U^T D^-1 U, which needs ONE operand buffer and no backward substitution
+//         (ekf_c.c:105,115 with K the exact gain reduce to this); during the predict its first rows hold the
+//         NFROWS x E exchange rows of F P;
+//   S/LT, Rm, small vectors.
 template <class M, class K>
 struct CtaSmem {
   static constexpr int E = M::EDIM, Z = K::ZDIM, Y = K::YDIM;
-  static constexpr int LD = E | 1;                 // odd: row and column sweeps are both conflict-free
-  static constexpr int HL = (Z + 3) & ~3;          // leading dimension of the HP / W buffers ([column][c]); multiple of the mma k = 4
+  static constexpr int NPK = E * (E + 1) / 2;
+  static constexpr int HL = (Z + 3) & ~3;          // leading dimension of U ([column][k]); multiple of the mma k = 4
   static constexpr int SL = Z | 1;
-  double P[E * LD];
-  double HP[E * HL];                               // (H_err P)[c][k] stored as HP[k * HL + c]
-  double W[E * HL];                                // S^-1 (H_err P), same layout (B operand of the rank-m update)
-  double S[Z * SL];                                // H_err P H_err^T (projected in place)
+  static constexpr int NU = (E * HL > M::NFROWS * E) ? E * HL : M::NFROWS * E;
+  double Ppk[NPK];
+  double U[NU];
+  double S[Z * SL];                                // H_err P H_err^T (projected in place); then LT: the L D L^T factor, transposed
   double Rm[Z * SL];                               // R (projected in place)
-  double LT[Z * SL];                               // LDL^T factor of S, transposed
-  double dinv[Z];
+  double dinv[HL];                                 // 1 / D[k], zero padded to HL
+  double yt[HL];                                   // L^-1 y
   double V[(K::HAS_HE ? K::EADIM : 1) * Z];        // Householder vectors of He
   double beta[K::HAS_HE ? K::EADIM : 1];
   double y[Z];
@@ -157,57 +166,82 @@ struct SmemCol {  // read-only view of one shared-memory column / row as a vecto
   __device__ __forceinline__ double operator[](int i) const { return p[i * stride]; }
 };
 
+// element (i, j) of the packed lower-triangular storage
+__device__ __forceinline__ int pk_idx(int i, int j) { return (i >= j) ? (i * (i + 1) / 2 + j) : (j * (j + 1) / 2 + i); }
+
+struct PackedCol {  // column `col` of the packed symmetric matrix as a vector (generated code indexes it with constants)
+  const double* p;
+  int col, tcol;    // tcol = col (col + 1) / 2
+  __device__ __forceinline__ double operator[](int i) const { return (i >= col) ? p[i * (i + 1) / 2 + col] : p[tcol + i]; }
+};
+
+// packed index -> (row, column)
+__device__ __forceinline__ void pk_unpack(int idx, int& i, int& j) {
+  i = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+  while (i * (i + 1) / 2 > idx) --i;
+  while ((i + 1) * (i + 2) / 2 <= idx) ++i;
+  j = idx - i * (i + 1) / 2;
+}
+
 // apply Q^T = H_r ... H_1 (Householder reflectors, vectors V[r][:], scalars beta[r]) to a Z-vector in registers
 template <int Z, int NR>
 __device__ __forceinline__ void apply_reflectors(const double* V, const double* beta, double (&u)[Z]) {
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
-    double w = 0.0;
+    double w0 = 0.0, w1 = 0.0;   // two partial sums: half the dependent-FMA chain
 #pragma unroll
-    for (int i = 0; i < Z; ++i) w = fma(V[r * Z + i], u[i], w);
-    w *= beta[r];
+    for (int i = 0; i < Z; i += 2) {
+      w0 = fma(V[r * Z + i], u[i], w0);
+      if (i + 1 < Z) w1 = fma(V[r * Z + i + 1], u[i + 1], w1);
+    }
+    const double w = (w0 + w1) * beta[r];
 #pragma unroll
     for (int i = 0; i < Z; ++i) u[i] = fma(-w, V[r * Z + i], u[i]);
   }
 }
 
 template <class M>
-constexpr int cta_tpg() { return ((M::EDIM + 31) / 32) * 32; }   // threads per group: one per column
-constexpr int CTA_GROUPS = 2;                                      // groups split the rows of the rank-m covariance update
+constexpr int cta_threads() { return ((M::EDIM + 31) / 32) * 32; }   // one thread per column
+#ifndef RNB_CTA_MIN_BLOCKS
+#define RNB_CTA_MIN_BLOCKS 4
+#endif
 
 template <class M, class K, bool PRED, bool UPD>
-__global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS, 2) ekf_step_cta(const StepArgs<M::NG> a, int o, const double* __restrict__ ws_all) {
+__global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step_cta(const StepArgs<M::NG> a, int o, const double* __restrict__ ws_all) {
   constexpr int D = M::DIM, E = M::EDIM, ME = M::MEDIM, Z = K::ZDIM, Y = K::YDIM, NR = Z - Y;
   using SM = CtaSmem<M, K>;
   using W = CtaWs<M, K>;
-  constexpr int LD = SM::LD, HL = SM::HL, SL = SM::SL;
+  constexpr int HL = SM::HL, SL = SM::SL, NPK = SM::NPK;
+  static_assert(ME <= 32, "FROW_MASK covers a main block of at most 32 error states");
+  static_assert(Y + 1 <= 32, "the innovation covariance is factored by one warp (one lane per column + one for y)");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SM& s = *reinterpret_cast<SM*>(smem_raw);
-  constexpr int TPG = cta_tpg<M>();
   const int tid = threadIdx.x, nth = blockDim.x;
-  const int grp = tid / TPG, col = tid - grp * TPG;   // group 0 does the per-column work, all groups share the big row loops
+  const int col = tid;
   const long long b = blockIdx.x;
   const double* ws = ws_all + b * W::SIZE;
   const long long fb = a.idx ? (long long)a.idx[b] : b;   // filter this entry works on
   double* Pg = a.P + fb * (long long)(E * E);
   const bool own = col < E;            // this thread is attached to column `col`
-  const bool own0 = own && grp == 0;   // ... and is the one that writes per-column results
+  const PackedCol pc{s.Ppk, own ? col : 0, own ? col * (col + 1) / 2 : 0};
 
-  // ---- stage: covariance tile (coalesced, re-pitched), leaf values ----
+  // ---- stage: lower triangle of the covariance (the matrix is symmetric: half the read traffic), leaf values ----
   {
-    // all loads of the tile are issued before the first shared-memory store (one global round trip, not one per pass)
-    constexpr int NIT = (E * E + TPG * CTA_GROUPS - 1) / (TPG * CTA_GROUPS);
+    constexpr int NIT = (NPK + cta_threads<M>() - 1) / cta_threads<M>();
     double v[NIT];
+    int i, j;
+    pk_unpack(tid, i, j);
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
+    for (int it = 0; it < NIT; ++it) {   // all loads are issued before the first shared-memory store (one global round trip)
       const int idx = it * nth + tid;
-      v[it] = (idx < E * E) ? Pg[idx] : 0.0;
+      v[it] = (idx < NPK) ? Pg[i * E + j] : 0.0;
+      j += nth;                          // advance (i, j) by nth packed positions
+      while (j > i) { j -= i + 1; ++i; }
     }
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int idx = it * nth + tid;
-      const int i = idx / E, j = idx - i * E;
-      if (idx < E * E) s.P[i * LD + j] = v[it];
+      if (idx < NPK) s.Ppk[idx] = v[it];
     }
   }
   for (int i = tid; i < D; i += nth) s.x[i] = ws[W::OFF_X + i];
@@ -224,61 +258,75 @@ __global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS, 2) ekf_step_cta(con
     }
     const double* Rg = a.R + ((a.flags & FLAG_SHARED_R) ? 0 : (b * a.n_obs + o) * (long long)(Z * Z));
     for (int idx = tid; idx < Z * Z; idx += nth) s.Rm[(idx / Z) * SL + idx % Z] = Rg[idx];
+    for (int i = tid; i < HL; i += nth) { s.dinv[i] = 0.0; s.yt[i] = 0.0; }
     if (tid == 0) s.gated = 0;
   }
   __syncthreads();
 
   // =============================== predict: P <- F P F^T + dt Q (main block) ===============================
   if constexpr (PRED) {
-    if (own0) {  // column col: (F P)[:, col]
+    double* T = s.U;                   // exchange rows: T[slot][column] = (F P)[frow(slot)][column]
+    if (own) {                         // column col of F P: only the rows of F that differ from the identity change
       double v[ME];
 #pragma unroll
-      for (int i = 0; i < ME; ++i) v[i] = s.P[i * LD + col];
+      for (int i = 0; i < ME; ++i) v[i] = pc[i];
       M::F_apply(s.fv, v);
-      M::frows_scatter(v, &s.P[col], LD);  // only the rows of F that differ from the identity change
+      M::frows_store(v, &T[col], E);
     }
     __syncthreads();
-    if (own0) {  // row col: ((F P) F^T)[col, :]
+    if (own && col < ME && ((M::FROW_MASK >> col) & 1u)) {   // row col of (F P) F^T, columns of the main block
+      const int slot = __popc(M::FROW_MASK & ((1u << col) - 1u));
       double v[ME];
 #pragma unroll
-      for (int k = 0; k < ME; ++k) v[k] = s.P[col * LD + k];
+      for (int k = 0; k < ME; ++k) {
+        // (F P)[col][k]: an exchange row if k is itself a changed row, else (symmetry of P) the exchange row's own entry
+        v[k] = T[slot * E + k];
+      }
       M::F_apply(s.fv, v);
-      M::frows_scatter(v, &s.P[col * LD], 1);
+      M::frows_scatter(v, &T[slot * E], 1);   // only the NFROWS x NFROWS block differs from T
+    }
+    __syncthreads();
+    if (own) {
+      int slot = 0;
+#pragma unroll
+      for (int r = 0; r < ME; ++r) {
+        if ((M::FROW_MASK >> r) & 1u) {
+          // element {r, col}: when both indices are changed rows it is visited from both sides -- the larger column writes
+          const bool other_side = (col < r) && ((M::FROW_MASK >> col) & 1u);
+          if (!other_side) s.Ppk[pk_idx(r, col)] = T[slot * E + col];
+          ++slot;
+        }
+      }
     }
     __syncthreads();
     {
       const double dt = s.dt;
       if (a.flags & FLAG_Q_DIAG) {
-        if (own0) s.P[col * LD + col] += dt * __ldg(a.Q + col * E + col);
+        if (own) s.Ppk[pc.tcol + col] += dt * __ldg(a.Q + col * E + col);
       } else {
-        for (int idx = tid; idx < E * E; idx += nth) {
-          const int i = idx / E, j = idx - i * E;
-          s.P[i * LD + j] = fma(dt, __ldg(a.Q + idx), s.P[i * LD + j]);
-        }
+        for (int i = 0; i < E; ++i)
+          for (int j = tid; j <= i; j += nth) s.Ppk[i * (i + 1) / 2 + j] = fma(dt, __ldg(a.Q + i * E + j), s.Ppk[i * (i + 1) / 2 + j]);
       }
     }
     __syncthreads();
     if (a.hP_pred) {
       double* Hg = a.hP_pred + fb * (long long)(E * E);
-      for (int idx = tid; idx < E * E; idx += nth) Hg[idx] = s.P[(idx / E) * LD + idx % E];
+      for (int idx = tid; idx < E * E; idx += nth) Hg[idx] = s.Ppk[pk_idx(idx / E, idx % E)];
     }
   }
 
   if constexpr (UPD) {
-    // ---- HP_raw[:, col] = H_err P[:, col] (sparse); every group keeps its own copy in registers ----
+    // ---- HP_raw[:, col] = H_err P[:, col] (sparse) ----
     double hp[Z];
     if (own) {
-      SmemCol<Z> pc{&s.P[col], LD};
       K::Herr_apply(s.hv, pc, hp);
-      if (grp == 0) {
 #pragma unroll
-        for (int c = 0; c < Z; ++c) s.HP[col * HL + c] = hp[c];  // unprojected, for S
-      }
+      for (int c = 0; c < Z; ++c) s.U[col * HL + c] = hp[c];  // unprojected, for S
     }
     __syncthreads();
     // S_raw[:, t] = H_err (HP_raw[t, :])^T   (P symmetric)
     if (tid < Z) {
-      SmemCol<Z> hr{&s.HP[tid], HL};
+      SmemCol<Z> hr{&s.U[tid], HL};
       double sc[Z];
       K::Herr_apply(s.hv, hr, sc);
 #pragma unroll
@@ -288,27 +336,32 @@ __global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS, 2) ekf_step_cta(con
     if constexpr (K::HAS_HE) {
       // project S and R on both sides, y and HP on the left; S and R are handled by two different warps
       const int w = tid >> 5, t = tid & 31;
-      if (w < 2 && t < Z) {  // columns
-        double* Mx = (w == 0) ? s.S : s.Rm;
-        double u[Z];
+      const int nw = nth >> 5;
+      for (int mx = w; mx < 2; mx += nw) {
+        if (t < Z) {  // columns
+          double* Mx = (mx == 0) ? s.S : s.Rm;
+          double u[Z];
 #pragma unroll
-        for (int c = 0; c < Z; ++c) u[c] = Mx[c * SL + t];
-        apply_reflectors<Z, NR>(s.V, s.beta, u);
+          for (int c = 0; c < Z; ++c) u[c] = Mx[c * SL + t];
+          apply_reflectors<Z, NR>(s.V, s.beta, u);
 #pragma unroll
-        for (int c = 0; c < Z; ++c) Mx[c * SL + t] = u[c];
+          for (int c = 0; c < Z; ++c) Mx[c * SL + t] = u[c];
+        }
       }
       if (own) apply_reflectors<Z, NR>(s.V, s.beta, hp);
       __syncthreads();
-      if (w < 2 && t < Z) {  // rows
-        double* Mx = (w == 0) ? s.S : s.Rm;
-        double u[Z];
+      for (int mx = w; mx < 2; mx += nw) {
+        if (t < Z) {  // rows
+          double* Mx = (mx == 0) ? s.S : s.Rm;
+          double u[Z];
 #pragma unroll
-        for (int c = 0; c < Z; ++c) u[c] = Mx[t * SL + c];
-        apply_reflectors<Z, NR>(s.V, s.beta, u);
+          for (int c = 0; c < Z; ++c) u[c] = Mx[t * SL + c];
+          apply_reflectors<Z, NR>(s.V, s.beta, u);
 #pragma unroll
-        for (int c = 0; c < Z; ++c) Mx[t * SL + c] = u[c];
+          for (int c = 0; c < Z; ++c) Mx[t * SL + c] = u[c];
+        }
       }
-      if (w == 2 && t == 0) {  // the innovation
+      if (tid == nth - 1) {  // the innovation (the last thread has no column when E is not a multiple of 32)
         double u[Z];
 #pragma unroll
         for (int c = 0; c < Z; ++c) u[c] = s.y[c];
@@ -319,164 +372,149 @@ __global__ void __launch_bounds__(cta_tpg<M>() * CTA_GROUPS, 2) ekf_step_cta(con
       __syncthreads();
     }
     // from here on only the trailing Y x Y block / Y entries are used (offset NR)
-    if (own0) {
-#pragma unroll
-      for (int c = 0; c < Y; ++c) s.HP[col * HL + c] = hp[NR + c];
-    }
 
-    // ---- factor S = S_raw + R (warp 0, lane j = column j), gate, refactor if gated ----
-    for (int pass = 0; pass < (K::MAHA ? 2 : 1); ++pass) {
-      if (tid < 32) {
-        const int j = tid < Y ? tid : 0;
-        double A[Y];
-        const double rs = (K::MAHA && pass == 1) ? 1.0e16 : 1.0;  // ekf_c.c:92
+    // ---- factor S + R = L D L^T by warp 0: lane j < Y = column j, lane Y carries y through the same eliminations
+    //      (so it ends as L^-1 y: the Mahalanobis distance and the state correction need nothing else).  The loop over
+    //      pivots is fully unrolled: register arrays are indexed statically and only rows below the pivot are touched.
+    //      Gate (ekf_c.c:88-94): if y^T S^-1 y exceeds the threshold, R is inflated by 1e16 and the factorisation redone.
+    if (tid < 32) {
+      const int j = tid < Y ? tid : 0;
+      double A0[Y], A1[K::MAHA ? Y : 1];
 #pragma unroll
-        for (int i = 0; i < Y; ++i) A[i] = s.S[(NR + i) * SL + NR + j] + rs * s.Rm[(NR + i) * SL + NR + j];
+      for (int i = 0; i < Y; ++i) {
+        const double sv = s.S[(NR + i) * SL + NR + j], rv = s.Rm[(NR + i) * SL + NR + j], yv = s.y[NR + i];
+        A0[i] = (tid == Y) ? yv : sv + rv;
+        if constexpr (K::MAHA) A1[i] = (tid == Y) ? yv : fma(1.0e16, rv, sv);   // ekf_c.c:92
+      }
+      __syncwarp();   // S is dead from here: its storage becomes LT
+      double* LT = s.S;
 #pragma unroll 1
-        for (int kk = 0; kk < Y; ++kk) {
-          // lane kk publishes its (unscaled) column; every lane needs c[lane] (= its own A[kk], symmetry) and c[i]
-          if (tid == kk) {
+      for (int pass = 0; pass < (K::MAHA ? 2 : 1); ++pass) {
+        double A[Y];
 #pragma unroll
-            for (int i = 0; i < Y; ++i) s.LT[kk * SL + i] = A[i];
+        for (int i = 0; i < Y; ++i) A[i] = (K::MAHA && pass == 1) ? A1[K::MAHA ? i : 0] : A0[i];
+#pragma unroll
+        for (int kk = 0; kk < Y; ++kk) {
+          if (tid == kk) {   // lane kk publishes its (unscaled) column: rows kk .. Y-1
+#pragma unroll
+            for (int i = kk; i < Y; ++i) LT[kk * SL + i] = A[i];
           }
           __syncwarp();
-          const double di = 1.0 / s.LT[kk * SL + kk];
+          const double di = 1.0 / LT[kk * SL + kk];
           if (tid == 0) s.dinv[kk] = di;
-          const double cj = s.LT[kk * SL + j] * di;
+          // L[lane][kk] = c[lane] / D[kk] (symmetry: c[lane] is the lane's own A[kk]); the y lane uses its own entry
+          const double cj = ((tid == Y) ? A[kk] : LT[kk * SL + j]) * di;
 #pragma unroll
-          for (int i = 0; i < Y; ++i)
-            if (i > kk) A[i] = fma(-s.LT[kk * SL + i], cj, A[i]);
+          for (int i = kk + 1; i < Y; ++i) A[i] = fma(-LT[kk * SL + i], cj, A[i]);
         }
         __syncwarp();
-        if (K::MAHA && pass == 0 && tid == 0) {
-          double u[Y];
+        bool gate = false;
+        if (tid == Y) {
+          double d = 0.0;   // y^T S^-1 y = sum_k (L^-1 y)_k^2 / D_k
 #pragma unroll
-          for (int i = 0; i < Y; ++i) u[i] = s.y[NR + i];
-#pragma unroll
-          for (int kk = 0; kk < Y; ++kk) {
-            const double uk = u[kk] * s.dinv[kk];
-#pragma unroll
-            for (int i = kk + 1; i < Y; ++i) u[i] = fma(-s.LT[kk * SL + i], uk, u[i]);
-          }
-          double d = 0.0;   // y^T S^-1 y = sum_k u_k^2 / D_k  (u = L^-1 y)
-#pragma unroll
-          for (int i = 0; i < Y; ++i) d = fma(u[i] * s.dinv[i], u[i], d);
-          s.gated = d > K::MAHA_THRESH;
+          for (int i = 0; i < Y; ++i) { d = fma(A[i] * s.dinv[i], A[i], d); s.yt[i] = A[i]; }
+          gate = K::MAHA && pass == 0 && d > K::MAHA_THRESH;
+          if (gate) s.gated = 1;
         }
+        gate = __shfl_sync(0xffffffffu, (int)gate, Y) != 0;
+        if (!gate) break;
+        __syncwarp();
       }
-      __syncthreads();
-      if (!(K::MAHA && pass == 0 && s.gated)) break;
     }
+    __syncthreads();
 
-    // ---- gain row: w = S^-1 HP[:, col] (every group, in registers); dx; covariance ----
-    double w[Y];
+    // ---- U[:, col] = L^-1 (A^T H_err P)[:, col]; state correction dx = U^T D^-1 (L^-1 y) ----
     if (own) {
+      const double* LT = s.S;
+      double u[Y];
 #pragma unroll
-      for (int c = 0; c < Y; ++c) w[c] = hp[NR + c];
+      for (int c = 0; c < Y; ++c) u[c] = hp[NR + c];
 #pragma unroll
       for (int kk = 0; kk < Y; ++kk) {
-        const double wk = w[kk] * s.dinv[kk];
+        const double uk = u[kk] * s.dinv[kk];
 #pragma unroll
-        for (int i = kk + 1; i < Y; ++i) w[i] = fma(-s.LT[kk * SL + i], wk, w[i]);
+        for (int i = kk + 1; i < Y; ++i) u[i] = fma(-LT[kk * SL + i], uk, u[i]);
       }
+      double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-      for (int i = 0; i < Y; ++i) w[i] *= s.dinv[i];
-      const volatile double* LTv = s.LT;
-#pragma unroll
-      for (int kk = Y - 2; kk >= 0; --kk) {
-        double acc = 0.0;
-#pragma unroll
-        for (int i = kk + 1; i < Y; ++i) acc = fma(LTv[kk * SL + i], w[i], acc);
-        w[kk] = fma(-acc, s.dinv[kk], w[kk]);
+      for (int c = 0; c < Y; c += 2) {
+        d0 = fma(u[c] * s.dinv[c], s.yt[c], d0);
+        if (c + 1 < Y) d1 = fma(u[c + 1] * s.dinv[c + 1], s.yt[c + 1], d1);
       }
-      if (grp == 0) {
-        double dxl = 0.0;
+      s.dx[col] = d0 + d1;
 #pragma unroll
-        for (int c = 0; c < Y; ++c) dxl = fma(w[c], s.y[NR + c], dxl);
-        s.dx[col] = dxl;
-      }
+      for (int c = 0; c < HL; ++c) s.U[col * HL + c] = (c < Y) ? u[c < Y ? c : 0] : 0.0;
     }
-    // ---- P -= HP^T W on the FP64 tensor path: 8 x 8 output tiles, k = Y padded to a multiple of 4 ----
-    if (own0) {
-#pragma unroll
-      for (int c = 0; c < HL; ++c) s.W[col * HL + c] = (c < Y) ? w[c < Y ? c : 0] : 0.0;
-#pragma unroll
-      for (int c = Y; c < HL; ++c) s.HP[col * HL + c] = 0.0;
-    }
-    __syncthreads();  // HP (projected) and W complete in shared memory
+    __syncthreads();
+    // ---- P -= U^T D^-1 U on the FP64 tensor path: lower-triangle 8 x 8 tiles only, k = Y padded to a multiple of 4 ----
     {
-      constexpr int NTE = (E + 7) / 8, NKY = HL / 4;
+      constexpr int NTE = (E + 7) / 8, NKY = HL / 4, NTRI = NTE * (NTE + 1) / 2;
       const int lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
       const int fg = lane >> 2, ft = lane & 3;
-      for (int tile = warp; tile < NTE * NTE; tile += nwarps) {
-        const int mi = tile / NTE, ni = tile - mi * NTE;
+      double nd[NKY];   // -1 / D[k] for this lane's k of every k-step
+#pragma unroll
+      for (int kq = 0; kq < NKY; ++kq) nd[kq] = -s.dinv[kq * 4 + ft];
+      for (int tile = warp; tile < NTRI; tile += nwarps) {
+        int mi, ni;
+        pk_unpack(tile, mi, ni);   // tiles enumerated like the packed elements: mi >= ni
         const int r = mi * 8 + fg, c = ni * 8 + 2 * ft, n = ni * 8 + fg;
-        double c0 = (r < E && c < E) ? s.P[r * LD + c] : 0.0;
-        double c1 = (r < E && c + 1 < E) ? s.P[r * LD + c + 1] : 0.0;
+        const bool ok0 = r < E && c <= r, ok1 = r < E && c + 1 <= r;   // inside the matrix and the lower triangle
+        const int p0 = r * (r + 1) / 2 + c;
+        double c0 = ok0 ? s.Ppk[p0] : 0.0;
+        double c1 = ok1 ? s.Ppk[p0 + 1] : 0.0;
+        double av[NKY], bv[NKY];
 #pragma unroll
         for (int kq = 0; kq < NKY; ++kq) {
-          const double av = (r < E) ? -s.HP[r * HL + kq * 4 + ft] : 0.0;   // A[m][k] = -(HP)^T
-          const double bv = (n < E) ? s.W[n * HL + kq * 4 + ft] : 0.0;     // B[k][n] = W
-          dmma884(c0, c1, av, bv);
+          av[kq] = (r < E) ? s.U[r * HL + kq * 4 + ft] * nd[kq] : 0.0;   // A[m][k] = -U[k][m] / D[k]
+          bv[kq] = (n < E) ? s.U[n * HL + kq * 4 + ft] : 0.0;            // B[k][n] = U[k][n]
         }
-        if (r < E && c < E) s.P[r * LD + c] = c0;
-        if (r < E && c + 1 < E) s.P[r * LD + c + 1] = c1;
+#pragma unroll
+        for (int kq = 0; kq < NKY; ++kq) dmma884(c0, c1, av[kq], bv[kq]);
+        if (ok0) s.Ppk[p0] = c0;
+        if (ok1) s.Ppk[p0 + 1] = c1;
       }
     }
-    // state injection (every thread evaluates the small generated function; identical values)
-    M::err_fun(s.x, s.dx, a.gv, s.xo);
     __syncthreads();
-    if ((a.flags & FLAG_NORM_AFTER_UPDATE) && a.n_quat > 0) {
-      if (tid == 0) for (int q = 0; q < a.n_quat; ++q) normalize4(s.xo + a.quat_idx[q]);
-      __syncthreads();
-    }
     const bool last = (o == a.n_obs - 1);
-    for (int i = tid; i < D; i += nth) {
-      if (last) a.x[fb * D + i] = s.xo[i];
-      const_cast<double*>(ws_all)[b * W::SIZE + W::OFF_X + i] = s.xo[i];  // next observation of this batch starts here
-      if (last && a.hx_filt) a.hx_filt[fb * D + i] = s.xo[i];
+    // state injection, normalisation and the small outputs by warp 0 while the other warps start writing P back
+    if (tid < 32) {
+      M::err_fun(s.x, s.dx, a.gv, s.xo);   // every lane evaluates the small generated function; identical values
+      __syncwarp();
+      if ((a.flags & FLAG_NORM_AFTER_UPDATE) && a.n_quat > 0) {
+        if (tid < a.n_quat) normalize4(s.xo + a.quat_idx[tid]);
+        __syncwarp();
+      }
+      for (int i = tid; i < D; i += 32) {
+        const double v = s.xo[i];
+        if (last) a.x[fb * D + i] = v;
+        const_cast<double*>(ws_all)[b * W::SIZE + W::OFF_X + i] = v;  // next observation of this batch starts here
+        if (last && a.hx_filt) a.hx_filt[fb * D + i] = v;
+      }
+      // innovation overwrites z (ekf_c.c:120): the first YDIM entries
+      for (int i = tid; i < Y; i += 32) a.z[(b * a.n_obs + o) * Z + i] = s.y[NR + i];
     }
-    // innovation overwrites z (ekf_c.c:120): the first YDIM entries
-    for (int i = tid; i < Y; i += nth) a.z[(b * a.n_obs + o) * Z + i] = s.y[NR + i];
     if (last && a.hP_filt) {
       double* Hg = a.hP_filt + fb * (long long)(E * E);
-      for (int idx = tid; idx < E * E; idx += nth) Hg[idx] = s.P[(idx / E) * LD + idx % E];
+      for (int idx = tid; idx < E * E; idx += nth) Hg[idx] = s.Ppk[pk_idx(idx / E, idx % E)];
     }
   }
 
-  __syncthreads();
-  for (int idx = tid; idx < E * E; idx += nth) {
-    const int i = idx / E, j = idx - i * E;
-    Pg[idx] = s.P[i * LD + j];
-  }
-}
-
-// per-instantiation device workspace
-inline double* cta_workspace(size_t doubles) {
-  static double* buf = nullptr;
-  static size_t cap = 0;
-  if (doubles > cap) {
-    if (buf) cudaFree(buf);
-    buf = nullptr; cap = 0;
-    if (!check(cudaMalloc(&buf, doubles * sizeof(double)), "cudaMalloc(cta workspace)")) return nullptr;
-    cap = doubles;
-  }
-  return buf;
+  for (int idx = tid; idx < E * E; idx += nth) Pg[idx] = s.Ppk[pk_idx(idx / E, idx % E)];
 }
 
 template <class M, class K, bool PRED, bool UPD>
 inline void launch_step_cta(const StepArgs<M::NG>& a, cudaStream_t st) {
   using W = CtaWs<M, K>;
-  double* ws = cta_workspace((size_t)a.B * W::SIZE);
-  if (!ws) return;
+  // leaf-value workspace of THIS call, allocated and released in stream order (calls on different streams / devices
+  // never share it)
+  double* ws = nullptr;
+  if (!check(cudaMallocAsync((void**)&ws, sizeof(double) * (size_t)a.B * W::SIZE, st), "cudaMallocAsync(cta workspace)")) return;
   constexpr size_t smem = sizeof(CtaSmem<M, K>);
-  static bool configured = false;
-  if (!configured) {
+  if (first_launch_of((const void*)ekf_step_cta<M, K, PRED, UPD>))
     check(cudaFuncSetAttribute(ekf_step_cta<M, K, PRED, UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute");
+  if (first_launch_of((const void*)ekf_step_cta<M, K, false, UPD>))
     check(cudaFuncSetAttribute(ekf_step_cta<M, K, false, UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute");
-    configured = true;
-  }
-  constexpr int threads = cta_tpg<M>() * CTA_GROUPS;
+  constexpr int threads = cta_threads<M>();
   const int n_obs = UPD ? a.n_obs : 1;
   for (int o = 0; o < n_obs; ++o) {
     const unsigned lgrid = (unsigned)((a.B + 63) / 64);
@@ -488,6 +526,7 @@ inline void launch_step_cta(const StepArgs<M::NG>& a, cudaStream_t st) {
       ekf_step_cta<M, K, false, UPD><<<(unsigned)a.B, threads, smem, st>>>(a, o, ws);
     }
   }
+  check(cudaFreeAsync(ws, st), "cudaFreeAsync(cta workspace)");
 }
 
 }  // namespace rnb
