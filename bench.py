@@ -31,10 +31,13 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 WORKLOADS = {
-  "live_1m": dict(filter="live", batch=1 << 20),
-  "live_100k": dict(filter="live", batch=100_000),
-  "kinematic_1m": dict(filter="kinematic", batch=1 << 20),
-  "kinematic_16m": dict(filter="kinematic", batch=1 << 24),   # 1.2 GB of state: larger than L2, a true HBM measurement
+  # BASELINE.json configs -> named workloads, each with its own JSON line (roofline of ITS dominant kernel)
+  "live_1m": dict(filter="live", batch=1 << 20, steps=200, warmup=5),           # the metric's headline config
+  "live_100k": dict(filter="live", batch=100_000, steps=200, warmup=5),         # config 3
+  "kinematic_1m": dict(filter="kinematic", batch=1 << 20, steps=200, warmup=5),  # config 2 (state fits L2: said so in the line)
+  "kinematic_16m": dict(filter="kinematic", batch=1 << 24, steps=100, warmup=5),  # 1.2 GB of state: larger than L2, a true HBM measurement
+  "live_rts": dict(filter="live", batch=125_000, steps=2, warmup=1),            # config 4: 1M / 8 GPUs = 125k per GPU, forward + RTS over a long history
+  "msckf_10k": dict(filter="msckf", batch=10_000, steps=100, warmup=5),         # config 5: triangulation + gated feature update + augment
 }
 LIVE_R = {4: [0.025**2] * 3, 10: [0.5**2] * 3, 12: [5.0**2] * 3}
 L2_BYTES = 126 << 20
@@ -151,6 +154,9 @@ def run_gpu(args):
       raise SystemExit("launch with torch.distributed.run for --gpus > 1")
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
+  from rednose_b200.sharding import bind_to_gpu_numa
+  orig_affinity = os.sched_getaffinity(0)
+  numa_node = bind_to_gpu_numa(local_rank)   # before any pinned allocation: staging buffers land on the GPU's socket
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 
@@ -216,6 +222,27 @@ def run_gpu(args):
     per_kind.setdefault(sched[args.warmup + j], []).append(ev[j][0].elapsed_time(ev[j][1]))
   assert bool(torch.isfinite(eng.x).all()), "filter diverged during the benchmark"
 
+  # ---- sustained figure: the same loop for >= args.sustain seconds (power-capped clocks, not a burst) ----
+  sustained = None
+  if args.sustain > 0:
+    n_s = max(args.steps, int(args.sustain * 1e3 / max(elapsed_ms / args.steps, 1e-3)))
+    sched_s = kind_schedule(fname, n_s)
+    with ClockSampler(local_rank) as clocks_s:
+      sync_all()
+      s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      s0.record()
+      for i in range(n_s):
+        one_step(i, sched_s[i])
+      s1.record()
+      sync_all()
+    sus_ms = s0.elapsed_time(s1)
+    if world > 1:
+      tmax = torch.tensor([sus_ms], dtype=torch.float64, device=dev)
+      dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+      sus_ms = float(tmax.item())
+    sustained = {"value": B * n_s * world / (sus_ms * 1e-3), "unit": "steps/s", "steps": n_s, "seconds": sus_ms * 1e-3, "clocks": clocks_s.summary()}
+    assert bool(torch.isfinite(eng.x).all())
+
   # ---- end to end through the public API: observations from pinned host memory, estimates back ----
   # HostStreamer.submit(t, kind, z_pinned_host, R) -> fused step -> x, y in pinned host memory, every step;
   # copies of consecutive steps overlap the kernel on separate streams.  P stays resident on the GPU.
@@ -253,6 +280,30 @@ def run_gpu(args):
   h2d = streamer.h2d_bytes / e2e_steps
   d2h = streamer.d2h_bytes / e2e_steps
   assert bool(torch.isfinite(streamer.x_host[0]).all())
+  # the same loop when the caller asks only for the pose columns back (HostStreamer(out_cols=...)): live_kf position + attitude
+  e2e_pose = None
+  if fname == "live":
+    del streamer
+    streamer = HostStreamer(eng, zdim, out_cols=range(7))
+    for i in range(3):
+      e2e_step(i, sched[i])
+    streamer.wait(); sync_all()
+    streamer.h2d_bytes = streamer.d2h_bytes = 0
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for j in range(e2e_steps):
+      e2e_step(j, sched[args.warmup + j])
+    streamer.wait()
+    torch.cuda.current_stream(dev).wait_stream(streamer.s_out)
+    p1.record()
+    sync_all()
+    pose_ms = p0.elapsed_time(p1)
+    if world > 1:
+      tmax = torch.tensor([pose_ms], dtype=torch.float64, device=dev)
+      dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+      pose_ms = float(tmax.item())
+    e2e_pose = {"value": B * e2e_steps * world / (pose_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": streamer.h2d_bytes / e2e_steps,
+                "d2h_bytes_per_step": streamer.d2h_bytes / e2e_steps, "what": "as e2e, but only state columns 0..6 (ECEF position + attitude quaternion) and the innovations come back"}
 
   # ---- the stateless C-ABI entry point with HOST buffers: <name>_host_step_<kind>(x, P, Q, ..., z, R, ...) copies the
   #      whole state in and out (what calling the reference's <name>_predict + <name>_update_<k> on caller-owned
@@ -298,6 +349,16 @@ def run_gpu(args):
     g1.record()
     sync_all()
     gather_ms = g0.elapsed_time(g1)
+    # ... and the covariances (x and P), in slices of filters so that the gathered copy fits beside the state
+    gp0, gp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    chunk = max(1, min(B, (8 << 30) // (world * edim * edim * 8)))
+    gp0.record()
+    for lo in range(0, B, chunk):
+      outP = gather_filters(eng.P[lo:lo + chunk], world * min(chunk, B - lo))
+    gp1.record()
+    sync_all()
+    gather_P_ms = gp0.elapsed_time(gp1)
+    del out, outP
 
   if rank == 0:
     peak, peak_kind = measured_peaks()
@@ -305,12 +366,13 @@ def run_gpu(args):
     dom_ms = float(np.mean(per_kind[dom]))
     algo = bytes_per_step(dim, edim, zdim[dom]) * B
     achieved = algo / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, "no ncu capture of this kernel at this batch size is committed"
     try:  # measured DRAM bytes per launch of this kernel from the committed ncu capture (same batch size only)
       with open(os.path.join(REPO, "profiles", "traffic.json"), encoding="utf-8") as f:
         tj = json.load(f)
-      if B == 1 << 20:
-        traffic = tj.get(f"ekf_step<{fname}, kind {dom}>")
+      key = f"ekf_step<{fname}, kind {dom}>"
+      if B == int(tj.get("batch", 1 << 20)) and key in tj:
+        traffic, traffic_src = tj[key], f"profiles/traffic.json ({tj.get('capture', 'ncu --set full capture')}), not measured in this run"
     except Exception:  # pylint: disable=broad-except
       pass
     if edim <= 6:
@@ -336,17 +398,26 @@ def run_gpu(args):
       "per_kind_ms": {str(k): float(np.mean(v)) for k, v in per_kind.items()},
       "roofline": {"bound": "hbm", "kernel": f"{kern}<{fname}, kind {dom}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                    "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_step": bytes_per_step(dim, edim, zdim[dom]), "algorithmic_bytes_per_launch": algo,
-                   "traffic": traffic},
+                   "traffic": traffic, "traffic_source": traffic_src},
       "e2e": {"value": B * e2e_steps * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
               "steps": e2e_steps, "d2h_GBps_per_gpu": d2h / (e2e_ms / e2e_steps * 1e-3) / 1e9, "h2d_GBps_per_gpu": h2d / (e2e_ms / e2e_steps * 1e-3) / 1e9,
               "what": "HostStreamer.submit(t, kind, z_pinned_host, R_kind): H2D of z, fused step, D2H of x and y into pinned host memory EVERY step (3 streams overlap consecutive steps); P stays resident; bound by the device-to-host link (d2h_GBps_per_gpu vs ~55-63 GB/s for PCIe Gen5 x16)"},
       "clocks": clocks.summary(),
     }
+    if e2e_pose is not None:
+      line["e2e_pose_columns_only"] = e2e_pose
     if host_abi is not None:
       line["e2e_stateless_host_c_abi"] = host_abi
     if gather_ms is not None:
       line["final_gather_ms"] = gather_ms
-    if not args.no_cpu_baseline and world == 1:
+      line["final_gather_P_ms"] = gather_P_ms
+      line["final_gather_what"] = f"NCCL all-gather of x [{world * B}, {dim}] ({world * B * dim * 8 / 1e6:.0f} MB) and of P [{world * B}, {edim}, {edim}] ({world * B * edim * edim * 8 / 1e9:.2f} GB, in slices)"
+    if sustained is not None:
+      line["sustained"] = sustained
+    line["numa_node"] = numa_node
+    line["timed_region"] = f"{args.steps} steps = {elapsed_ms:.1f} ms: a burst figure; 'sustained' repeats the loop for >= {args.sustain} s"
+    if not args.no_cpu_baseline:
+      os.sched_setaffinity(0, orig_affinity)   # the CPU arm may use every core the container has, not only the GPU's socket
       line["cpu_baseline"] = cpu_reference(fname, args.workload, budget_s=args.cpu_budget)
     if args.extras and world == 1:
       del eng, streamer, dpools
@@ -355,9 +426,368 @@ def run_gpu(args):
         line["extras"] = run_extras(dev, peak)
       except Exception as ex:  # pylint: disable=broad-except
         line["extras"] = {"error": repr(ex)[:300]}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
   if world > 1:
+    dist.barrier()   # the other ranks wait here while rank 0 times the CPU baseline
     dist.destroy_process_group()
+
+
+
+# ------------------------------------------------- BASELINE config 4: forward + RTS over a long history ---
+def _dist_setup(args):
+  import torch
+  import torch.distributed as dist
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if world != args.gpus and world == 1 and args.gpus > 1:
+    raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  from rednose_b200.sharding import bind_to_gpu_numa
+  orig = os.sched_getaffinity(0)
+  numa = bind_to_gpu_numa(local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  return torch, dist, rank, world, local_rank, dev, numa, orig
+
+
+def _max_over_ranks(torch, dist, world, dev, vals):
+  if world == 1:
+    return [float(v) for v in vals]
+  t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+  dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  return [float(v) for v in t.tolist()]
+
+
+def run_rts(args):
+  """live_kf sharded over the GPUs (125 000 filters per GPU = 1M over 8), forward filter + RTS smoother over a T-step
+  history (--rts-steps, 10 000 in BASELINE.json; default 1 000 so that the default run takes a minute; cost is linear in T).
+  The 81 MB per filter of a 10k-step history never materialises: CheckpointedSmoother keeps a checkpoint every `segment`
+  steps, re-filters one segment with history and smooths it (rednose_b200/smoothing.py).  One bench "step" = one complete
+  forward + backward job over the whole history; `value` = smoothed filter-steps per second (each one costs a plain fused
+  step, a fused step that records history, and one RTS backward step)."""
+  torch, dist, rank, world, local_rank, dev, numa, orig_aff = _dist_setup(args)
+  from rednose_b200.filters import ensure_generated
+  from rednose_b200.filters.live import LiveKalman
+  from rednose_b200.smoothing import CheckpointedSmoother
+  if local_rank == 0:
+    ensure_generated(LiveKalman)
+  if world > 1:
+    dist.barrier()
+  d = ensure_generated(LiveKalman)
+  B, T, S = (args.batch or WORKLOADS["live_rts"]["batch"]), args.rts_steps, args.rts_segment
+  x0, P0, Q, pools, (dim, edim), quat = make_problem("live", B, seed=4321 + rank, lib_dir=d)
+  x0d = torch.as_tensor(x0).to(dev)
+  P0d = torch.as_tensor(P0).to(dev).expand(B, -1, -1)
+  # observations in pinned HOST memory (two realisations per kind), copied to the device inside the timed region every step
+  hz = {k: [torch.as_tensor(np.ascontiguousarray(z[j])).pin_memory() for j in range(z.shape[0])] for k, (z, _) in pools.items()}
+  Rk = {k: torch.as_tensor(R[0]).to(dev) for k, (_, R) in pools.items()}
+  zdev = torch.empty(B, 3, dtype=torch.float64, device=dev)
+  sched = kind_schedule("live", T)
+  counters = {"h2d": 0, "d2h": 0}
+
+  def obs_fn(k, lo, hi):
+    kind = sched[k]
+    src = hz[kind][k % len(hz[kind])]
+    zdev[lo:hi].copy_(src[lo:hi], non_blocking=True)
+    counters["h2d"] += (hi - lo) * 3 * 8
+    return 0.01 * (k + 1), kind, zdev[lo:hi], Rk[kind]
+
+  cs = CheckpointedSmoother(d, "live", Q, dim, edim, quaternion_idxs=quat, device=dev, hbm_budget_bytes=int(args.hbm_budget_gb) << 30, segment=S)
+  tile = min(cs.tile_size(T), B)
+  # smoothed pose columns go back to pinned host memory, segment by segment (the result a caller keeps; P stays on the device)
+  pose_cols = 7
+  host_out = torch.empty(min(S + 1, T), tile, pose_cols, dtype=torch.float64).pin_memory()
+  stage = torch.empty(min(S + 1, T), tile, pose_cols, dtype=torch.float64, device=dev)
+  chk = {"finite": True, "n": 0}
+
+  def sink(lo, hi, k0, xs, Ps):
+    n = xs.shape[0]
+    stage[:n, :hi - lo].copy_(xs[:, :, :pose_cols])
+    host_out[:n, :hi - lo].copy_(stage[:n, :hi - lo], non_blocking=True)
+    counters["d2h"] += n * (hi - lo) * pose_cols * 8
+    chk["n"] += n * (hi - lo)
+    if k0 == 0:
+      chk["finite"] = chk["finite"] and bool(torch.isfinite(xs[0]).all()) and bool(torch.isfinite(Ps[0]).all())
+
+  def sync_all():
+    torch.cuda.synchronize(dev)
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize(dev)
+
+  # warm-up: a short history through the same objects (allocations, attribute setup), then W full-length passes only if asked
+  Tw = min(T, 2 * S + 3)
+  cs.run(x0d, P0d, Tw, obs_fn, sink, norm_quats=True)
+  sync_all()
+  from rednose_b200.batched import BatchedEKF  # noqa: F401  (launch counter lives on the engine)
+  launches0 = cs._engine.launches
+  counters["h2d"] = counters["d2h"] = 0
+  chk["n"] = 0
+  acc = {"forward_ms": 0.0, "reforward_with_history_ms": 0.0, "backward_ms": 0.0}
+  t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  with ClockSampler(local_rank) as clocks:
+    sync_all()
+    t0.record()
+    for _ in range(args.steps):
+      cs.run(x0d, P0d, T, obs_fn, sink, norm_quats=True)
+      for k_ in acc:
+        acc[k_] += cs.stats[k_]
+    t1.record()
+    sync_all()
+  elapsed_ms, fwd_ms, refwd_ms, bwd_ms = _max_over_ranks(torch, dist, world, dev, [t0.elapsed_time(t1), acc["forward_ms"], acc["reforward_with_history_ms"], acc["backward_ms"]])
+  launches = cs._engine.launches - launches0
+  assert chk["finite"] and chk["n"] == B * T * args.steps, (chk, B * T * args.steps)
+  if rank == 0:
+    peak, peak_kind = measured_peaks()
+    K = args.steps
+    nseg = cs.stats["segments"]
+    bwd_steps = B * (T - 1) * K                       # backward recursions (the last step of the history only starts it)
+    refwd_steps = B * (T + nseg - 1) * K              # each segment re-filters one extra step (the next segment's first)
+    ach = 12176 * bwd_steps / (bwd_ms * 1e-3) / 1e9
+    line = {
+      "metric": "RTS-smoothed filter-steps/s (forward filter + checkpointed re-filter with history + RTS backward pass, float64)",
+      "value": B * T * K * world / (elapsed_ms * 1e-3), "unit": "steps/s",
+      "n_gpus": world, "steps": K, "warmup": 1, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "f64", "data": "synthetic",
+      "config": {"workload": "live_rts", "filter": "live", "filters_per_gpu": B, "history_steps": T, "baseline_history_steps": 10_000,
+                 "extrapolation": "cost is linear in history_steps (per-step rates below); --rts-steps 10000 runs BASELINE.json's length",
+                 "segment_steps": S, "segments": nseg, "tile_filters": cs.stats["tile_filters"], "tiles_per_pass": cs.stats["tiles"],
+                 "hbm_bytes_per_filter": cs.stats["bytes_per_filter"], "full_history_bytes_per_filter": 8 * (2 * edim * edim + 2 * dim + 1) * T,
+                 "kind_schedule": "kinds 4/10 alternating + kind 12 every 100 steps (first step is a position fix)", "norm_quats": True,
+                 "l2": "inputs larger than L2", "sharding": "independent filters per GPU, no data-path collective"},
+      "gpu_launches": launches,
+      "phases": {"forward_steps_per_s": B * T * K / (fwd_ms * 1e-3), "reforward_with_history_steps_per_s": refwd_steps / (refwd_ms * 1e-3),
+                 "backward_steps_per_s": bwd_steps / (bwd_ms * 1e-3), "forward_ms": fwd_ms, "reforward_with_history_ms": refwd_ms, "backward_ms": bwd_ms,
+                 "other_ms": elapsed_ms - fwd_ms - refwd_ms - bwd_ms,
+                 "reforward_frac_of_peak": (8240 + 8120) * refwd_steps / (refwd_ms * 1e-3) / 1e9 / peak, "forward_frac_of_peak": 8240 * B * T * K / (fwd_ms * 1e-3) / 1e9 / peak},
+      "roofline": {"bound": "hbm", "kernel": "ekf_rts_warp_mma<live>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_kind,
+                   "algorithmic_bytes_per_step": 12176, "traffic": None, "traffic_source": "see profiles/ (ncu capture of the backward kernel)",
+                   "note": "the backward step is ~45k FP64 FMA per filter-step (LDL^T, two triangular solves, two 24^3 products): at 64 FMA/clk/SM that alone is ~0.7 of this HBM roofline, so the kernel is FP64-pipe/latency bound, not bandwidth bound (DESIGN.md)"},
+      "e2e": {"value": B * T * K * world / (elapsed_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": counters["h2d"] / K, "d2h_bytes_per_step": counters["d2h"] / K,
+              "what": "the timed region IS end to end: every step's observations are copied from pinned host memory (twice: both forward passes) and the smoothed pose columns of every step go back to pinned host memory"},
+      "clocks": clocks.summary(), "numa_node": numa,
+    }
+    if not args.no_cpu_baseline:
+      os.sched_setaffinity(0, orig_aff)
+      line["cpu_baseline"] = cpu_rts_reference(budget_s=args.cpu_budget)
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def cpu_rts_reference(budget_s=15.0, T=40):
+  """The reference's path for config 4 on the host: forward filter (oracle C, all usable cores) + rts_smooth, which the
+  reference only has in Python/numpy (ekf_sym.py:651-690) -- timed one filter at a time, as shipped."""
+  from oracle import build_ref
+  from oracle.handle import Oracle
+  from oracle.rts_numpy import rts_smooth
+  o = Oracle(build_ref.OUT, "live")
+  x, P, Q, pools, (dim, edim), quat = _cpu_problem("live", 8)
+  P = np.tile(P, (8, 1, 1))
+  sched = kind_schedule("live", T)
+  hx_p, hx_f, hP_p, hP_f = [], [], [], []
+  t0 = time.perf_counter()
+  for k in range(T):
+    xp, Pp = o.predict(x, P, Q, 0.01)
+    for q in xp:
+      q[3:7] /= np.linalg.norm(q[3:7])
+    zp, R = pools[sched[k]]
+    x, P, _ = o.update(sched[k], xp, Pp, zp[k % 2], R)
+    for q in x:
+      q[3:7] /= np.linalg.norm(q[3:7])
+    hx_p.append(xp); hP_p.append(Pp); hx_f.append(x.copy()); hP_f.append(P.copy())
+  t_fwd = time.perf_counter() - t0
+  ts = 0.01 * (1 + np.arange(T))
+  t1 = time.perf_counter()
+  n = 0
+  while n < 8 and time.perf_counter() - t1 < budget_s:
+    rts_smooth(o, np.stack(hx_p)[:, n], np.stack(hx_f)[:, n], np.stack(hP_p)[:, n], np.stack(hP_f)[:, n], ts, 23, 22, norm_quats=True)
+    n += 1
+  t_bwd = time.perf_counter() - t1
+  per_step = t_bwd / (n * (T - 1))
+  return {"value": 1.0 / per_step, "unit": "steps/s", "cores": 1, "kind": "port", **_cpu_info(),
+          "sample": f"{n} filters x {T - 1} backward steps of rts_smooth (numpy + cffi leaf calls, one filter at a time: the reference has no batched or C smoother)",
+          "backward_steps_per_s_one_core": 1.0 / per_step, "what": "oracle/rts_numpy.py = restatement of rednose/helpers/ekf_sym.py:651-690 on the oracle library's leaf functions"}
+
+
+# ---------------------------------------- BASELINE config 5: MSCKF, feature tracks with Mahalanobis rejection ---
+def run_msckf(args):
+  """10 000 MSCKF filters (live main state + 10 cloned camera poses, DIM 93 / EDIM 82).  One step = one camera frame:
+  triangulate the tracked point from its 10 observations (compute_pos_batch, the front-end of SURVEY.md 8f-3), fused
+  predict + null-space-projected, Mahalanobis-gated feature update with that point as extra_args, then augment (clone
+  window shift).  5 % of the tracks are gross outliers (x50 noise) so that the gate fires."""
+  torch, dist, rank, world, local_rank, dev, numa, orig_aff = _dist_setup(args)
+  from rednose_b200.batched import BatchedEKF
+  from rednose_b200.features import FeatureFrontend, to_c_matrix
+  from rednose_b200.filters import ensure_generated
+  from rednose_b200.filters.msckf import DIM, EDIM, MsckfKalman
+  if local_rank == 0:
+    ensure_generated(MsckfKalman); FeatureFrontend(10)
+  if world > 1:
+    dist.barrier()
+  d = ensure_generated(MsckfKalman)
+  fe = FeatureFrontend(10)
+  B = args.batch or WORKLOADS["msckf_10k"]["batch"]
+  g = torch.Generator(device=dev); g.manual_seed(77 + rank)
+  f64 = dict(dtype=torch.float64, device=dev)
+
+  def quat2rot_t(q):
+    w, x, y, z = q.unbind(-1)
+    return torch.stack([w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (w * y + x * z),
+                        2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
+                        2 * (x * z - w * y), 2 * (w * x + y * z), w * w - x * x - y * y + z * z], -1).reshape(q.shape[:-1] + (3, 3))
+
+  # initial state: the vehicle drives forward at 10 m/s, camera frames every 0.05 s -> clones 0.5 m apart
+  dt, speed = 0.05, 10.0
+  x0 = torch.as_tensor(MsckfKalman.initial_x).to(dev).repeat(B, 1)
+  q = torch.randn(B, 4, generator=g, **f64); q = q / q.norm(dim=1, keepdim=True)
+  Rm = quat2rot_t(q)
+  x0[:, 0:3] += torch.randn(B, 3, generator=g, **f64) * 100.0
+  x0[:, 3:7] = q
+  x0[:, 7:10] = Rm[:, :, 0] * speed
+  for c in range(10):
+    o = 23 + 7 * c
+    x0[:, o:o + 3] = x0[:, 0:3] - Rm[:, :, 0] * (speed * dt) * (10 - c)
+    x0[:, o + 3:o + 7] = q
+  pd = np.concatenate([[25.0] * 3 + [0.05**2] * 3 + [1.0] * 3 + [0.1**2] * 3 + [0.01**2] * 3 + [0.01**2] + [0.5**2] * 3 + [0.01**2] * 3] + [[1.0] * 3 + [0.02**2] * 3] * 10)
+  eng = BatchedEKF(d, "msckf", MsckfKalman.Q, x0, np.diag(pd), device=dev, quaternion_idxs=[3] + [26 + 7 * c for c in range(10)])
+  sigma = 1e-3
+  Rk = torch.eye(20, **f64) * sigma**2
+  to_c = torch.as_tensor(to_c_matrix().reshape(9)).to(dev)
+  z_host = torch.empty(B, 20, dtype=torch.float64).pin_memory()
+  x_host = torch.empty(B, DIM, dtype=torch.float64).pin_memory()
+  stats = {"gated": 0, "tracks": 0}
+
+  def make_obs():
+    """a new landmark 15-50 m ahead of the newest clone, projected into the 10 clones (+ noise, 5 % gross outliers)"""
+    clones = eng.x[:, 23:].reshape(B, 10, 7)
+    Rl = quat2rot_t(clones[:, 9, 3:7])
+    local = torch.stack([torch.rand(B, generator=g, **f64) * 35 + 15, torch.rand(B, generator=g, **f64) * 10 - 5, torch.rand(B, generator=g, **f64) * 6 - 3], 1)
+    point = clones[:, 9, 0:3] + torch.einsum('bij,bj->bi', Rl, local)
+    pc = torch.einsum('bcji,bcj->bci', quat2rot_t(clones[:, :, 3:7]), point[:, None, :] - clones[:, :, 0:3])   # R^T (p - pos)
+    z = torch.stack([pc[:, :, 1] / pc[:, :, 0], pc[:, :, 2] / pc[:, :, 0]], -1).reshape(B, 20)
+    noise = torch.randn(B, 20, generator=g, **f64) * sigma
+    out = torch.rand(B, generator=g, device=dev) < 0.05
+    noise[out] *= 50.0
+    return (z + noise).contiguous(), out
+
+  def hot_path(z):
+    poses = eng.x[:, 23:].contiguous()                     # the 10 clones ARE the poses of the track: [B, 70]
+    pos, param, iters = fe.compute_pos_batch(to_c, poses, z)
+    eng.step(17, dt, z, Rk, ea=pos)                         # the kernel overwrites z with the (projected) innovation
+    eng.augment()
+    return pos
+
+  def sync_all():
+    torch.cuda.synchronize(dev)
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize(dev)
+
+  for _ in range(args.warmup):
+    z, _o = make_obs()
+    hot_path(z)
+  sync_all()
+  K = args.steps
+  ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+  launches0 = eng.launches
+  tr0 = None
+  with ClockSampler(local_rank) as clocks:
+    sync_all()
+    for j in range(K):
+      z, outl = make_obs()                                  # synthetic camera frame: NOT part of the timed hot path
+      tr_before = torch.einsum('bii->b', eng.P[:, 22:, 22:])
+      ev[j][0].record()
+      hot_path(z)
+      ev[j][1].record()
+      stats["tracks"] += B
+    sync_all()
+  hot_ms = sum(a.elapsed_time(b) for a, b in ev)
+  (hot_ms,) = _max_over_ranks(torch, dist, world, dev, [hot_ms])
+  launches = eng.launches - launches0 + K   # + compute_pos per frame
+  assert bool(torch.isfinite(eng.x).all()) and bool(torch.isfinite(eng.P).all()), "MSCKF diverged during the benchmark"
+  # how often the gate fires (one extra un-timed frame, read off the clone block of the covariance)
+  z, outl = make_obs()
+  poses = eng.x[:, 23:].contiguous()
+  pos, _, iters = fe.compute_pos_batch(to_c, poses, z)
+  maha_before = torch.einsum('bii->b', eng.P[:, 22:, 22:]).clone()
+  eng.step(17, dt, z.clone(), Rk, ea=pos)
+  gated = (torch.einsum('bii->b', eng.P[:, 22:, 22:]) > maha_before * (1 - 1e-9))
+  eng.augment()
+  # ---- e2e: observations from pinned host memory in, state estimate out, every frame ----
+  e2e_K = min(K, 20)
+  frames = []
+  for _ in range(e2e_K):
+    zf, _o = make_obs()
+    frames.append(zf.cpu().pin_memory())
+    hot_path(zf)
+  eng.init_state(x0, torch.as_tensor(np.diag(pd)).to(dev), None)
+  zd = torch.empty(B, 20, **f64)
+  sync_all()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for j in range(e2e_K):
+    zd.copy_(frames[j], non_blocking=True)
+    hot_path(zd)
+    x_host.copy_(eng.x, non_blocking=True)
+  e1.record()
+  sync_all()
+  (e2e_ms,) = _max_over_ranks(torch, dist, world, dev, [e0.elapsed_time(e1)])
+  if rank == 0:
+    peak, peak_kind = measured_peaks()
+    bs = 8 * (2 * EDIM * EDIM + 2 * DIM + 20 + 400 + 17 + 3 + 1)
+    step_ms = hot_ms / K
+    line = {
+      "metric": "MSCKF camera-frame steps/s (triangulation + fused predict + gated feature update + augment, float64)",
+      "value": B * K * world / (hot_ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": step_ms,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+      "config": {"workload": "msckf_10k", "filter": "msckf", "filters_per_gpu": B, "dim": DIM, "edim": EDIM, "clones": 10, "zdim": 20, "projected_dim": 17,
+                 "outlier_fraction": 0.05, "gated_fraction_measured": float(gated.double().mean()), "outliers_among_gated": float((outl & gated).sum() / max(1, int(gated.sum()))),
+                 "gauss_newton_iterations_mean": float(iters.double().mean()),
+                 "l2": f"state {B * EDIM * EDIM * 8 / 2**20:.0f} MiB of P vs 126 MiB of L2: {'larger than L2' if B * EDIM * EDIM * 8 > L2_BYTES else 'FITS in L2'}",
+                 "timing": "CUDA events around the hot-path calls of every frame; the synthetic observation generator between frames is excluded",
+                 "sharding": "independent filters per GPU, no data-path collective"},
+      "gpu_launches": launches,
+      "roofline": {"bound": "hbm", "kernel": "ekf_step_cta<msckf, kind 17> (+ leaf, compute_pos, augment in the same timed region)", "achieved": bs * B / (step_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                   "frac": bs * B / (step_ms * 1e-3) / 1e9 / peak, "peak_source": peak_kind, "algorithmic_bytes_per_step": bs, "traffic": None,
+                   "traffic_source": "see profiles/ (ncu capture of ekf_step_cta)"},
+      "e2e": {"value": B * e2e_K * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": B * 20 * 8, "d2h_bytes_per_step": B * DIM * 8, "steps": e2e_K,
+              "what": "per frame: z [B, 20] from pinned host memory, compute_pos + fused step + augment, x [B, 93] back to pinned host memory; P stays resident"},
+      "clocks": clocks.summary(), "numa_node": numa,
+    }
+    if not args.no_cpu_baseline:
+      os.sched_setaffinity(0, orig_aff)
+      line["cpu_baseline"] = cpu_msckf_reference(budget_s=args.cpu_budget)
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def cpu_msckf_reference(budget_s=15.0):
+  """reference-generated MSCKF C (dense 82 x 82 Joseph form, full-pivot LU kernel of He) on all usable host cores."""
+  from oracle import build_ref
+  from oracle.handle import Oracle
+  from tests.util import msckf_batch, msckf_feature_obs
+  o = Oracle(build_ref.OUT, "msckf")
+  cores = _threads()
+  Bs = 64 * cores
+  x, P, Q, point = msckf_batch(Bs, seed=5)
+  z, R, _ = msckf_feature_obs(o, x, point, seed=6, outlier_frac=0.05)
+  quats = [3] + [26 + 7 * c for c in range(10)]
+  o.batch_step(17, x[:cores], P[:cores], Q, 0.01, z[:cores], R[:cores], ea=point[:cores], quat_idxs=quats, flags=3, nthreads=cores)
+  t = time.perf_counter()
+  n = 0
+  while time.perf_counter() - t < budget_s and n < 20:
+    o.batch_step(17, x, P, Q, 0.01, z, R, ea=point, quat_idxs=quats, flags=3, nthreads=cores)
+    n += 1
+  el = time.perf_counter() - t
+  return {"value": Bs * n / el, "unit": "steps/s", "cores": cores, "threads": cores, "kind": "port", **_cpu_info(),
+          "sample": f"{Bs} filters x {n} fused feature steps (predict + update_17), {el:.1f} s; includes the harness's array copies (~0.1 MB per filter-step against ~2 Mflop of dense algebra)",
+          "what": "reference-generated leaf C + Eigen-free restatement of ekf_c.c, g++ -O2; compute_pos / augment not included (they are negligible beside the dense 82^3 products)"}
 
 
 # ------------------------------------------------------------------ secondary kernels (extras) ---
@@ -750,22 +1180,38 @@ def run_reference(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=200)
-  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--steps", type=int, default=None, help="timed steps (default: the workload's own)")
+  ap.add_argument("--warmup", type=int, default=None)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--workload", default="live_1m", choices=sorted(WORKLOADS))
   ap.add_argument("--batch", type=int, default=0, help="override filters per GPU")
   ap.add_argument("--e2e-steps", type=int, default=20)
   ap.add_argument("--cpu-budget", type=float, default=15.0)
+  ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained figure beside the K-step burst (0 = skip)")
+  ap.add_argument("--rts-steps", type=int, default=1000, help="live_rts: history length T (BASELINE.json: 10000)")
+  ap.add_argument("--rts-segment", type=int, default=50, help="live_rts: steps between checkpoints")
+  ap.add_argument("--hbm-budget-gb", type=float, default=140.0, help="live_rts: HBM the smoother may use per GPU")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-extras", dest="extras", action="store_false",
                   help="skip the short measurements of the other kernels (kinematic / history / RTS / ragged / MSCKF, ~1 min)")
   ap.add_argument("--extras", dest="extras", action="store_true", default=True)
   args = ap.parse_args()
-  args.warmup = max(args.warmup, 3)
+  wl = WORKLOADS[args.workload]
+  if args.steps is None:
+    args.steps = wl["steps"]
+  if args.warmup is None:
+    args.warmup = wl["warmup"]
   if args.impl == "reference":
+    args.warmup = max(args.warmup, 3)
     run_reference(args)
+  elif args.workload == "live_rts":
+    args.warmup = max(args.warmup, 1)
+    run_rts(args)
+  elif args.workload == "msckf_10k":
+    args.warmup = max(args.warmup, 3)
+    run_msckf(args)
   else:
+    args.warmup = max(args.warmup, 3)
     run_gpu(args)
 
 

@@ -242,18 +242,23 @@ class BatchedEKF:
     dt = t - self.filter_time
     y = self.step(kind, dt, z, R, ea, hist_pred=(hist.x_pred[k], hist.P_pred[k]), hist_filt=(hist.x_filt[k], hist.P_filt[k]))
     self.filter_time = t
-    hist.t[k] = t
+    hist.t_host[k] = float(t)
     hist.n += 1
     return y
 
-  def rts_smooth(self, hist, norm_quats=False, quaternion_idxs=(3,), in_place=False, out=None):
+  def rts_smooth(self, hist, norm_quats=False, quaternion_idxs=(3,), in_place=False, out=None, terminal=None, k0=0):
     """Batched RTS backward pass over a recorded history (ekf_sym.py:651-690, one launch for all filters).
 
     Returns (xs [T, B, DIM], Ps [T, B, EDIM, EDIM]) on the device.  `norm_quats` normalises the quaternion(s)
     at `quaternion_idxs` the way the reference normalises its hard-coded slice 3:7.
+
+    `terminal=(x [B, DIM], P [B, EDIM, EDIM])` smooths one SEGMENT of a longer history (steps k0 .. k0 + T - 2): the
+    recursion starts from that smoothed estimate of step k0 + T - 1, whose history entry (the last one recorded) only
+    contributes its predicted state; its row of xs / Ps is not written.
     """
     T = hist.n
     assert T >= 1
+    hist.sync_times()
     if out is not None:
       xs, Ps = out                      # caller-provided [T, B, DIM] / [T, B, EDIM, EDIM] buffers
     else:
@@ -261,9 +266,17 @@ class BatchedEKF:
       Ps = hist.P_filt if in_place else torch.empty_like(hist.P_filt)
     qi = self._ffi.new("int[]", list(quaternion_idxs) or [0])
     with torch.cuda.device(self.device):
-      getattr(self._lib, f"{self.name}_batch_rts")(
-        self._cp(hist.x_pred), self._cp(hist.P_pred), self._cp(hist.x_filt), self._cp(hist.P_filt), self._cp(hist.t), 0,
-        self._p(xs), self._p(Ps), T, self.B, qi, len(quaternion_idxs) if norm_quats else 0, 1 if norm_quats else 0, self._stream())
+      if terminal is None:
+        getattr(self._lib, f"{self.name}_batch_rts")(
+          self._cp(hist.x_pred), self._cp(hist.P_pred), self._cp(hist.x_filt), self._cp(hist.P_filt), self._cp(hist.t), 0,
+          self._p(xs), self._p(Ps), T, self.B, qi, len(quaternion_idxs) if norm_quats else 0, 1 if norm_quats else 0, self._stream())
+      else:
+        xt, Pt = terminal
+        assert xt.is_contiguous() and Pt.is_contiguous() and xt.shape == (self.B, self.dim_x) and Pt.shape == (self.B, self.dim_err, self.dim_err)
+        getattr(self._lib, f"{self.name}_batch_rts_segment")(
+          self._cp(hist.x_pred), self._cp(hist.P_pred), self._cp(hist.x_filt), self._cp(hist.P_filt), self._cp(hist.t), 0,
+          self._p(xs), self._p(Ps), T, self.B, qi, len(quaternion_idxs) if norm_quats else 0, 1 if norm_quats else 0,
+          self._cp(xt), self._cp(Pt), int(k0), self._stream())
     self.launches += 1
     self._check("batch_rts")
     return xs[:T], Ps[:T]
@@ -280,6 +293,11 @@ class History:
     self.P_pred = torch.empty(T, B, dim_err, dim_err, **kw)
     self.P_filt = torch.empty(T, B, dim_err, dim_err, **kw)
     self.t = torch.zeros(T, **kw)
+    self.t_host = np.zeros(T)          # step times are collected on the host and uploaded once, before the backward pass
+    self._t_pinned = None
+
+  def sync_times(self):
+    self.t.copy_(torch.as_tensor(self.t_host))
 
   def bytes(self):
     return sum(t.numel() * 8 for t in (self.x_pred, self.x_filt, self.P_pred, self.P_filt, self.t))

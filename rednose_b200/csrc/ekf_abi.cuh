@@ -195,9 +195,11 @@ inline void batch_maha(HostCtx<M>& ctx, const double* x, const double* P, const 
 template <class M>
 inline void batch_rts(HostCtx<M>& ctx, const double* hx_pred, const double* hP_pred, const double* hx_filt, const double* hP_filt,
                       const double* t, int t_per_filter, double* xs, double* Ps, int T, long long B,
-                      const int* quat_idxs, int n_quat, int norm_quats, void* stream) {
+                      const int* quat_idxs, int n_quat, int norm_quats, void* stream,
+                      const double* x_term = nullptr, const double* P_term = nullptr, long long k0 = 0) {
   RtsArgs<M::NG> a;
   memset(&a, 0, sizeof(a));
+  a.x_term = (x_term && P_term) ? x_term : nullptr; a.P_term = (x_term && P_term) ? P_term : nullptr; a.k0 = k0;
   a.hx_pred = hx_pred; a.hP_pred = hP_pred; a.hx_filt = hx_filt; a.hP_filt = hP_filt;
   a.t = t; a.t_per_filter = t_per_filter; a.xs = xs; a.Ps = Ps; a.T = T; a.B = B; a.norm_quats = norm_quats;
   a.n_quat = n_quat < 0 ? 0 : (n_quat > MAX_QUAT ? MAX_QUAT : n_quat);

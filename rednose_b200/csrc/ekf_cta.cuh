@@ -225,25 +225,48 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
   const bool own = col < E;            // this thread is attached to column `col`
   const PackedCol pc{s.Ppk, own ? col : 0, own ? col * (col + 1) / 2 : 0};
 
-  // ---- stage: lower triangle of the covariance (the matrix is symmetric: half the read traffic), leaf values ----
+  // ---- stage: lower triangle of the covariance (the matrix is symmetric: half the read traffic), leaf values.
+  //      Warp w takes rows w, w + nw, ...; lanes run along the row (coalesced); RB rows are in flight per round trip. ----
+  const int lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
+  constexpr int NC = (E + 31) / 32;     // 32-column chunks of a row
   {
-    constexpr int NIT = (NPK + cta_threads<M>() - 1) / cta_threads<M>();
-    double v[NIT];
-    int i, j;
-    pk_unpack(tid, i, j);
+    constexpr int RB = 9;
+    for (int i0 = warp; i0 < E; i0 += nw * RB) {
+      double v[RB][NC];
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {   // all loads are issued before the first shared-memory store (one global round trip)
-      const int idx = it * nth + tid;
-      v[it] = (idx < NPK) ? Pg[i * E + j] : 0.0;
-      j += nth;                          // advance (i, j) by nth packed positions
-      while (j > i) { j -= i + 1; ++i; }
-    }
+      for (int rr = 0; rr < RB; ++rr) {
+        const int i = i0 + rr * nw;
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int idx = it * nth + tid;
-      if (idx < NPK) s.Ppk[idx] = v[it];
+        for (int c = 0; c < NC; ++c) {
+          const int j = lane + 32 * c;
+          v[rr][c] = (i < E && j <= i) ? Pg[i * E + j] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < RB; ++rr) {
+        const int i = i0 + rr * nw;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int j = lane + 32 * c;
+          if (i < E && j <= i) s.Ppk[i * (i + 1) / 2 + j] = v[rr][c];
+        }
+      }
     }
   }
+  // packed -> full row-major matrix in global memory (P itself and the history slabs): coalesced rows, no divisions
+  int tj[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) tj[c] = (lane + 32 * c) * (lane + 32 * c + 1) / 2;
+  auto store_full = [&](double* __restrict__ dst) {
+    for (int i = warp; i < E; i += nw) {
+      const int ti = i * (i + 1) / 2;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int j = lane + 32 * c;
+        if (j < E) dst[i * E + j] = s.Ppk[(j <= i) ? ti + j : tj[c] + i];
+      }
+    }
+  };
   for (int i = tid; i < D; i += nth) s.x[i] = ws[W::OFF_X + i];
   if constexpr (PRED) {
     for (int i = tid; i < (M::NF > 0 ? M::NF : 1); i += nth) s.fv[i] = ws[W::OFF_FV + i];
@@ -309,10 +332,7 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
       }
     }
     __syncthreads();
-    if (a.hP_pred) {
-      double* Hg = a.hP_pred + fb * (long long)(E * E);
-      for (int idx = tid; idx < E * E; idx += nth) Hg[idx] = s.Ppk[pk_idx(idx / E, idx % E)];
-    }
+    if (a.hP_pred) store_full(a.hP_pred + fb * (long long)(E * E));
   }
 
   if constexpr (UPD) {
@@ -335,8 +355,7 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
     __syncthreads();
     if constexpr (K::HAS_HE) {
       // project S and R on both sides, y and HP on the left; S and R are handled by two different warps
-      const int w = tid >> 5, t = tid & 31;
-      const int nw = nth >> 5;
+      const int w = warp, t = lane;
       for (int mx = w; mx < 2; mx += nw) {
         if (t < Z) {  // columns
           double* Mx = (mx == 0) ? s.S : s.Rm;
@@ -448,15 +467,16 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
     __syncthreads();
     // ---- P -= U^T D^-1 U on the FP64 tensor path: lower-triangle 8 x 8 tiles only, k = Y padded to a multiple of 4 ----
     {
-      constexpr int NTE = (E + 7) / 8, NKY = HL / 4, NTRI = NTE * (NTE + 1) / 2;
-      const int lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+      constexpr int NTE = (E + 7) / 8, NKY = HL / 4;
       const int fg = lane >> 2, ft = lane & 3;
       double nd[NKY];   // -1 / D[k] for this lane's k of every k-step
 #pragma unroll
       for (int kq = 0; kq < NKY; ++kq) nd[kq] = -s.dinv[kq * 4 + ft];
-      for (int tile = warp; tile < NTRI; tile += nwarps) {
-        int mi, ni;
-        pk_unpack(tile, mi, ni);   // tiles enumerated like the packed elements: mi >= ni
+      int tcount = 0, next = warp;   // lower-triangle tiles (mi >= ni) dealt to the warps round-robin
+      for (int mi = 0; mi < NTE; ++mi)
+      for (int ni = 0; ni <= mi; ++ni, ++tcount) {
+        if (tcount != next) continue;
+        next += nw;
         const int r = mi * 8 + fg, c = ni * 8 + 2 * ft, n = ni * 8 + fg;
         const bool ok0 = r < E && c <= r, ok1 = r < E && c + 1 <= r;   // inside the matrix and the lower triangle
         const int p0 = r * (r + 1) / 2 + c;
@@ -493,13 +513,10 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
       // innovation overwrites z (ekf_c.c:120): the first YDIM entries
       for (int i = tid; i < Y; i += 32) a.z[(b * a.n_obs + o) * Z + i] = s.y[NR + i];
     }
-    if (last && a.hP_filt) {
-      double* Hg = a.hP_filt + fb * (long long)(E * E);
-      for (int idx = tid; idx < E * E; idx += nth) Hg[idx] = s.Ppk[pk_idx(idx / E, idx % E)];
-    }
+    if (last && a.hP_filt) store_full(a.hP_filt + fb * (long long)(E * E));
   }
 
-  for (int idx = tid; idx < E * E; idx += nth) Pg[idx] = s.Ppk[pk_idx(idx / E, idx % E)];
+  store_full(Pg);
 }
 
 template <class M, class K, bool PRED, bool UPD>

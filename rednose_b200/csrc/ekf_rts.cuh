@@ -44,6 +44,15 @@ struct RtsArgs {
   int norm_quats;
   int n_quat;
   int quat_idx[MAX_QUAT];
+  // segment continuation (checkpointed smoothing of long histories): when x_term / P_term are given, the slabs hold
+  // the steps k0 .. k0 + T - 1 of a longer history, entry T - 1 only contributes its PREDICTED state, and the recursion
+  // starts from x_term [B, DIM] / P_term [B, EDIM, EDIM] = the smoothed estimate of step k0 + T - 1 produced by the
+  // segment behind it (instead of the reference's start from the predicted last state, ekf_sym.py:658-659); entry T - 1
+  // of xs / Ps is then not written.  k0 only decides which outputs get their quaternion normalised (all but global
+  // index 0, ekf_sym.py:666-667).
+  const double* x_term;
+  const double* P_term;
+  long long k0;
   double gv[NG > 0 ? NG : 1];
 };
 
@@ -98,18 +107,21 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp(con
   double pn[N];  // column `lane` of the carried smoothed covariance (main block)
   {
     const long long k = a.T - 1;
-    const double* Pg = a.hP_pred + k * BP + b * (long long)(E * E) + col;
+    const bool seg = a.x_term != nullptr;
+    const double* Pg = (seg ? a.P_term + b * (long long)(E * E) : a.hP_pred + k * BP + b * (long long)(E * E)) + col;
     double* Po = a.Ps + k * BP + b * (long long)(E * E) + col;
 #pragma unroll
     for (int i = 0; i < E; ++i) {
       const double v = Pg[i * E];
       if (i < N) pn[i] = v;
-      if (actE) Po[i * E] = v;
+      if (actE && !seg) Po[i * E] = v;
     }
-    for (int i = lane; i < D; i += 32) s.xn[i] = a.hx_pred[k * BX + b * D + i];
+    for (int i = lane; i < D; i += 32) s.xn[i] = seg ? a.x_term[b * D + i] : a.hx_pred[k * BX + b * D + i];
     __syncwarp();
-    if (a.norm_quats && a.T >= 2) normalize_xn();
-    for (int i = lane; i < D; i += 32) a.xs[k * BX + b * D + i] = s.xn[i];
+    if (!seg) {
+      if (a.norm_quats && a.T >= 2) normalize_xn();
+      for (int i = lane; i < D; i += 32) a.xs[k * BX + b * D + i] = s.xn[i];
+    }
   }
 
 #pragma unroll 1
@@ -203,7 +215,7 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp(con
     __syncwarp();
     for (int i = lane; i < D; i += 32) s.xn[i] = (i < D1) ? s.xt[i] : s.xf[i];
     __syncwarp();
-    if (a.norm_quats && k >= 1) normalize_xn();
+    if (a.norm_quats && k + a.k0 >= 1) normalize_xn();
     for (int i = lane; i < D; i += 32) a.xs[k * BX + b * D + i] = s.xn[i];
 
     // ---- covariance: P_{k|N} = P_{k|k} + X^T (dP X) ----

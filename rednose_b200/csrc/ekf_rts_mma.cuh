@@ -79,9 +79,10 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp_mma
   double pn[NT * NT * 2];
   {
     const long long k = a.T - 1;
-    const double* Pg = a.hP_pred + k * BP + b * (long long)(E * E);
+    const bool seg = a.x_term != nullptr;   // segment continuation: start from the smoothed estimate handed in
+    const double* Pg = seg ? a.P_term + b * (long long)(E * E) : a.hP_pred + k * BP + b * (long long)(E * E);
     double* Po = a.Ps + k * BP + b * (long long)(E * E);
-    for (int idx = lane; idx < E * E; idx += 32) Po[idx] = Pg[idx];
+    if (!seg) for (int idx = lane; idx < E * E; idx += 32) Po[idx] = Pg[idx];
 #pragma unroll
     for (int mi = 0; mi < NT; ++mi)
 #pragma unroll
@@ -91,10 +92,12 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp_mma
         if (r < N && c < N) v = *reinterpret_cast<const double2*>(Pg + r * E + c);
         pn[(mi * NT + ni) * 2] = v.x; pn[(mi * NT + ni) * 2 + 1] = v.y;
       }
-    for (int i = lane; i < D; i += 32) s.xn[i] = a.hx_pred[k * BX + b * D + i];
+    for (int i = lane; i < D; i += 32) s.xn[i] = seg ? a.x_term[b * D + i] : a.hx_pred[k * BX + b * D + i];
     __syncwarp();
-    if (a.norm_quats && a.T >= 2) normalize_xn();
-    for (int i = lane; i < D; i += 32) a.xs[k * BX + b * D + i] = s.xn[i];
+    if (!seg) {
+      if (a.norm_quats && a.T >= 2) normalize_xn();
+      for (int i = lane; i < D; i += 32) a.xs[k * BX + b * D + i] = s.xn[i];
+    }
   }
 
 #pragma unroll 1
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp_mma
     __syncwarp();
     for (int i = lane; i < D; i += 32) s.xn[i] = (i < D1) ? s.xt[i] : s.xf[i];
     __syncwarp();
-    if (a.norm_quats && k >= 1) normalize_xn();
+    if (a.norm_quats && k + a.k0 >= 1) normalize_xn();
     for (int i = lane; i < D; i += 32) a.xs[k * BX + b * D + i] = s.xn[i];
 
     // ---- X into shared memory, row-major, zero padded (lane j writes column j) ----

@@ -42,3 +42,44 @@ def gather_filters(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
   if all(s == pad for s in sizes):
     return out
   return torch.cat([out[r * pad:r * pad + sizes[r]] for r in range(world)])
+
+
+def gpu_numa_cpus(device_index: int):
+  """(numa_node, sorted CPU list) of the host socket GPU `device_index` hangs off, or (None, None) if unknown.
+  Read from sysfs through the GPU's PCI address (no nvidia-smi dependency)."""
+  try:
+    import torch
+    bus = torch.cuda.get_device_properties(device_index)
+    pci = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+    with open(f"/sys/bus/pci/devices/{pci}/numa_node", encoding="utf-8") as f:
+      node = int(f.read().strip())
+    if node < 0:
+      return None, None
+    with open(f"/sys/devices/system/node/node{node}/cpulist", encoding="utf-8") as f:
+      spec = f.read().strip()
+    cpus = []
+    for part in spec.split(","):
+      a, _, b = part.partition("-")
+      cpus.extend(range(int(a), int(b or a) + 1))
+    return node, sorted(cpus)
+  except (OSError, ValueError, AttributeError, RuntimeError):
+    return None, None
+
+
+def bind_to_gpu_numa(device_index: int):
+  """Pin this process (one process per GPU) to the CPUs of the GPU's NUMA node, so that pinned staging buffers
+  allocated afterwards are first-touched on the socket the GPU's PCIe root belongs to and the per-step host<->device
+  copies of 8 ranks do not cross the inter-socket link.  Returns the node bound to, or None (left unbound)."""
+  import os
+  node, cpus = gpu_numa_cpus(device_index)
+  if node is None:
+    return None
+  try:
+    allowed = os.sched_getaffinity(0)
+    target = allowed & set(cpus)
+    if not target:
+      return None
+    os.sched_setaffinity(0, target)
+    return node
+  except (OSError, AttributeError):
+    return None

@@ -70,3 +70,97 @@ class TiledSmoother:
       sink(lo, hi, xs, Ps)
       tiles += 1
     return tiles
+
+
+class CheckpointedSmoother:
+  """Forward filter + RTS smoother over histories too long to store, for LARGE tiles of filters.
+
+  Tiling over filters alone (TiledSmoother) trades history length for batch size: BASELINE.json config 4 (10 000 steps)
+  would leave ~1 500 filters per launch, which cannot fill 148 SMs.  Here only a CHECKPOINT (x, P: 4 kB per live filter)
+  is kept every `segment` steps of a first forward pass; the backward sweep then visits the segments last to first,
+  re-runs the forward filter of one segment from its checkpoint WITH history (segment + 1 steps: the extra one is the
+  first step of the segment behind it, whose predicted state the recursion needs) and smooths it starting from the
+  smoothed estimate handed over by that segment (`<name>_batch_rts_segment`).  Memory per filter is
+  T / segment checkpoints + one segment of history instead of T steps of history, so ~100k live filters fit one tile;
+  the price is a second forward pass.  The kernels are deterministic, so the result is bit-identical to smoothing the
+  whole history at once (tests/test_parity_gpu.py::test_checkpointed_smoother_equals_full_history)."""
+
+  def __init__(self, folder, name, Q, dim_x, dim_err, quaternion_idxs=(), device="cuda", hbm_budget_bytes=120 << 30, segment=64, tile=None):
+    self.folder, self.name, self.Q = folder, name, Q
+    self.dim_x, self.dim_err = dim_x, dim_err
+    self.quat = tuple(quaternion_idxs)
+    self.device = torch.device(device)
+    self.budget, self.segment, self.tile = hbm_budget_bytes, int(segment), tile
+    self._engine = self._hist = self._ck = None
+    self.stats = {}
+
+  def bytes_per_filter(self, T):
+    nseg = (T + self.segment - 1) // self.segment
+    state = 8 * (self.dim_err**2 + self.dim_x)
+    return nseg * state + history_bytes_per_filter(self.dim_x, self.dim_err, self.segment + 1) + 3 * state
+
+  def tile_size(self, T):
+    return self.tile or max(1, int(self.budget // self.bytes_per_filter(T)))
+
+  def run(self, x0, P0, T, obs_fn, sink, norm_quats=False, t0=0.0):
+    """obs_fn(k, lo, hi) -> (t, kind, z, R) must return the SAME observation every time it is asked for step k (each step
+    is filtered twice) in a buffer the kernel may overwrite.  sink(lo, hi, k0, xs [n, tile, DIM], Ps [n, tile, EDIM, EDIM])
+    receives the smoothed steps k0 .. k0 + n - 1 of filters lo..hi (segments arrive last to first; views valid during
+    the call only).  Returns the number of tiles."""
+    B, S = x0.shape[0], self.segment
+    n_tile = min(self.tile_size(T), B)
+    nseg = (T + S - 1) // S
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    fwd_ms = refwd_ms = bwd_ms = 0.0
+    tiles = 0
+    for lo in range(0, B, n_tile):
+      hi = min(lo + n_tile, B)
+      n = hi - lo
+      if self._engine is None or self._engine.B != n:
+        self._engine = BatchedEKF(self.folder, self.name, self.Q, x0[lo:hi], P0[lo:hi], device=self.device, quaternion_idxs=self.quat)
+        self._hist = self._engine.new_history(S + 1)
+        self._ck = (torch.empty(nseg, n, self.dim_x, dtype=torch.float64, device=self.device),
+                    torch.empty(nseg, n, self.dim_err, self.dim_err, dtype=torch.float64, device=self.device))
+        self._term = (torch.empty(n, self.dim_x, dtype=torch.float64, device=self.device),
+                      torch.empty(n, self.dim_err, self.dim_err, dtype=torch.float64, device=self.device))
+      else:
+        self._engine.init_state(x0[lo:hi], P0[lo:hi], None)
+      eng, hist, (ck_x, ck_P), (tx, tP) = self._engine, self._hist, self._ck, self._term
+      if ck_x.shape[0] != nseg:
+        ck_x = torch.empty(nseg, n, self.dim_x, dtype=torch.float64, device=self.device)
+        ck_P = torch.empty(nseg, n, self.dim_err, self.dim_err, dtype=torch.float64, device=self.device)
+        self._ck = (ck_x, ck_P)
+      ck_t = [t0] * nseg
+      # ---- pass 1: forward without history, checkpoint before the first step of every segment ----
+      eng.filter_time = t0
+      ev[0].record()
+      for k in range(T):
+        if k % S == 0:
+          ck_x[k // S].copy_(eng.x); ck_P[k // S].copy_(eng.P); ck_t[k // S] = eng.filter_time
+        t, kind, z, R = obs_fn(k, lo, hi)
+        eng.predict_and_update_batch(t, kind, z, R)
+      ev[1].record(); ev[1].synchronize(); fwd_ms += ev[0].elapsed_time(ev[1])
+      # ---- pass 2: segments last to first: forward with history from the checkpoint, then backward ----
+      have_term = False
+      for j in range(nseg - 1, -1, -1):
+        k0 = j * S
+        k1 = min(k0 + S + 1, T)          # one step past the segment unless it is the last
+        eng.x.copy_(ck_x[j]); eng.P.copy_(ck_P[j]); eng.filter_time = ck_t[j]
+        hist.n = 0
+        ev[0].record()
+        for k in range(k0, k1):
+          t, kind, z, R = obs_fn(k, lo, hi)
+          eng.step_recorded(hist, kind, t, z, R)
+        ev[1].record(); ev[1].synchronize(); refwd_ms += ev[0].elapsed_time(ev[1])
+        ev[0].record()
+        xs, Ps = eng.rts_smooth(hist, norm_quats=norm_quats, quaternion_idxs=self.quat or (3,), in_place=True,
+                                terminal=(tx, tP) if have_term else None, k0=k0)
+        ev[1].record(); ev[1].synchronize(); bwd_ms += ev[0].elapsed_time(ev[1])
+        n_valid = (k1 - k0) - (1 if have_term else 0)
+        tx.copy_(xs[0]); tP.copy_(Ps[0])   # smoothed estimate of step k0: where the segment in front of this one starts
+        have_term = True
+        sink(lo, hi, k0, xs[:n_valid], Ps[:n_valid])
+      tiles += 1
+    self.stats = {"tiles": tiles, "tile_filters": n_tile, "segments": nseg, "segment_steps": S, "forward_ms": fwd_ms, "reforward_with_history_ms": refwd_ms,
+                  "backward_ms": bwd_ms, "bytes_per_filter": self.bytes_per_filter(T)}
+    return tiles

@@ -18,8 +18,11 @@ import torch
 
 
 class HostStreamer:
-  def __init__(self, engine, zdims: dict[int, int], depth: int = 2):
+  def __init__(self, engine, zdims: dict[int, int], depth: int = 2, out_cols=None, every: int = 1):
+    """out_cols: state columns copied back to the host each step (None = the whole state; e.g. range(7) for pose only);
+    every: copy the estimate back only every `every`-th step (innovations always come back)."""
     self.e = engine
+    self.every = max(1, int(every))
     dev = engine.device
     self.depth = depth
     self.s_in = torch.cuda.Stream(dev)
@@ -28,7 +31,10 @@ class HostStreamer:
     kw = dict(dtype=torch.float64, device=dev)
     self.z_dev = {k: [torch.empty(B, 1, m, **kw) for _ in range(depth)] for k, m in zdims.items()}
     self.x_snap = [torch.empty(B, D, **kw) for _ in range(depth)]
-    self.x_host = [torch.empty(B, D, dtype=torch.float64).pin_memory() for _ in range(depth)]
+    self.cols = None if out_cols is None else torch.as_tensor(list(out_cols), dtype=torch.long, device=dev)
+    Dout = D if self.cols is None else int(self.cols.numel())
+    self.x_sel = None if self.cols is None else [torch.empty(B, Dout, **kw) for _ in range(depth)]
+    self.x_host = [torch.empty(B, Dout, dtype=torch.float64).pin_memory() for _ in range(depth)]
     self.y_host = {k: [torch.empty(B, 1, m, dtype=torch.float64).pin_memory() for _ in range(depth)] for k, m in zdims.items()}
     self.ev_in = [torch.cuda.Event() for _ in range(depth)]
     self.ev_done = [torch.cuda.Event() for _ in range(depth)]
@@ -55,12 +61,18 @@ class HostStreamer:
     e.filter_time = t
     self.ev_done[slot].record(main)
     self.s_out.wait_event(self.ev_done[slot])
+    send_x = (self.k % self.every) == 0
     with torch.cuda.stream(self.s_out):
-      self.x_host[slot].copy_(self.x_snap[slot], non_blocking=True)
+      if send_x:
+        if self.cols is None:
+          self.x_host[slot].copy_(self.x_snap[slot], non_blocking=True)
+        else:
+          torch.index_select(self.x_snap[slot], 1, self.cols, out=self.x_sel[slot])
+          self.x_host[slot].copy_(self.x_sel[slot], non_blocking=True)
       self.y_host[kind][slot].copy_(self.z_dev[kind][slot], non_blocking=True)
       self.ev_out[slot].record(self.s_out)
     self.h2d_bytes += z_host.numel() * 8
-    self.d2h_bytes += (self.x_host[slot].numel() + self.y_host[kind][slot].numel()) * 8
+    self.d2h_bytes += ((self.x_host[slot].numel() if send_x else 0) + self.y_host[kind][slot].numel()) * 8
     self.k += 1
     return self.k - 1
 

@@ -127,3 +127,83 @@ def test_msckf_two_observations_per_predict_and_gather_list(msckf_dirs):
   assert rel_err(got_x[sel], xs) < 1e-9 and rel_err(got_P[sel], Ps) < 1e-8
   keep = np.setdiff1d(np.arange(B), sel)
   assert np.array_equal(got_x[keep], x[keep]) and np.array_equal(got_P[keep], P[keep])
+
+
+def test_msckf_he_leaf_matches_reference_generated_c(msckf_dirs):
+  """The exported He_<kind> leaf (d h / d point, ekf_sym.py:86-87) against the reference generator's own C."""
+  from rednose_b200.ekf_sym import EKF_sym
+  from rednose_b200.filters.msckf import MsckfKalman
+  gen_dir, oracle_dir = msckf_dirs
+  o = Oracle(oracle_dir, "msckf")
+  x, P, Q, point = msckf_batch(5, seed=21)
+  kf = EKF_sym(gen_dir, "msckf", Q, x[0], P[0], 23, 22, N=10, dim_augment=7, dim_augment_err=6, maha_test_kinds=[17], quaternion_idxs=QUATS)
+  for b in range(5):
+    want, got = np.zeros(60), np.zeros(60)
+    o.leaf("He_17", np.ascontiguousarray(x[b]), np.ascontiguousarray(point[b]), want)
+    kf.Hes[17](np.ascontiguousarray(x[b]), np.ascontiguousarray(point[b]), got)
+    assert np.max(np.abs(got - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+
+
+def test_msckf_projected_innovation_is_pinned_basis_invariantly(msckf_dirs):
+  """The innovation returned by a feature kind is expressed in a basis of the left null space of He (Eigen's
+  fullPivLu().kernel() in the reference, ekf_c.c:71; orthonormal Householder columns here), so its entries differ;
+  its length does not: for an orthonormal basis A, |A^T y|^2 = |(I - He He^+) y|^2, computed here from the reference
+  generator's own h_17 / He_17."""
+  gen_dir, oracle_dir = msckf_dirs
+  o = Oracle(oracle_dir, "msckf")
+  B = 64
+  x, P, Q, point = msckf_batch(B, seed=23)
+  z, R, _ = msckf_feature_obs(o, x, point, seed=24, sigma=2e-3)
+  e = _engine(gen_dir, x, P, Q, norm_after_update=False)
+  y = e.update(17, z, R, ea=point).cpu().numpy()[:, 0]
+  for b in range(B):
+    hx, He = np.zeros(20), np.zeros(60)
+    o.leaf("h_17", np.ascontiguousarray(x[b]), np.ascontiguousarray(point[b]), hx)
+    o.leaf("He_17", np.ascontiguousarray(x[b]), np.ascontiguousarray(point[b]), He)
+    He = He.reshape(20, 3)
+    yr = z[b] - hx
+    proj = yr - He @ np.linalg.lstsq(He, yr, rcond=None)[0]
+    assert abs(np.linalg.norm(y[b, :17]) - np.linalg.norm(proj)) <= 1e-9 * np.linalg.norm(proj)
+
+
+def test_msckf_baseline_size_10k_gate_fires_on_the_oracle_set(msckf_dirs):
+  """BASELINE.json config 5 at size: 10 000 filters, 5 % gross outliers (x50 noise), fused predict + gated feature
+  update + augment.  Every filter is compared with the oracle (16 host threads' worth of work: a few seconds); the set
+  of gated filters -- read off the covariance, which a gated update leaves essentially untouched -- must be the oracle's."""
+  gen_dir, oracle_dir = msckf_dirs
+  o = Oracle(oracle_dir, "msckf")
+  B = 10_000
+  x, P, Q, point = msckf_batch(B, seed=31)
+  xp, Pp = o.predict(x[:256], P[:256], Q, 0.01)
+  z, R, out = msckf_feature_obs(o, x, point, seed=32, sigma=1e-3, outlier_frac=0.05)
+  xr, Pr, _ = o.batch_step(17, x, P, Q, 0.01, z, R, ea=point, quat_idxs=QUATS, flags=3)
+  e = _engine(gen_dir, x, P, Q)
+  e.step(17, 0.01, z, R, ea=point)
+  gx, gP = e.state(), e.covs()
+  assert rel_err(gx, xr) < 1e-9 and rel_err(gP, Pr) < 1e-7
+  # per-filter, so that one bad filter cannot hide behind the batch maximum
+  ex = np.max(np.abs(gx - xr), axis=1) / np.max(np.abs(xr), axis=1)
+  eP = np.max(np.abs(gP - Pr), axis=(1, 2)) / np.max(np.abs(Pr), axis=(1, 2))
+  assert ex.max() < 1e-9 and eP.max() < 1e-6, (ex.max(), eP.max())
+  tr = lambda A: np.trace(A[:, 22:, 22:], axis1=1, axis2=2)
+  o_gated = tr(Pr) > tr(P) * (1 - 1e-9)          # clone block untouched (the predict does not change it, ekf_c.c:23-26)
+  g_gated = tr(gP) > tr(P) * (1 - 1e-9)
+  assert np.array_equal(o_gated, g_gated) and 100 < o_gated.sum() < 1500 and np.all(out[o_gated])
+  e.augment()
+  assert np.array_equal(e.covs()[:, -6:, -6:], gP[:, :6, :6])   # the new clone is the main pose (ekf_sym.py:384-389)
+
+
+def test_msckf_feature_kind_single_filter_host_entry_point(msckf_dirs):
+  """Single-filter host-pointer entry point <name>_update_<feature kind> (B = 1 launch of the CTA kernel, the only
+  kernel with the He projection: feature kinds are routed there whatever EDIM is, ekf_abi.cuh launch_step)."""
+  from rednose_b200.ekf_sym import EKF_sym
+  gen_dir, oracle_dir = msckf_dirs
+  o = Oracle(oracle_dir, "msckf")
+  x, P, Q, point = msckf_batch(3, seed=41)
+  z, R, _ = msckf_feature_obs(o, x, point, seed=42)
+  xr, Pr, _ = o.update(17, x, P, z, R, ea=point)
+  for b in range(3):
+    kf = EKF_sym(gen_dir, "msckf", Q, x[b], P[b], 23, 22, N=10, dim_augment=7, dim_augment_err=6, maha_test_kinds=[17], quaternion_idxs=QUATS)
+    xb, Pb, zb = x[b].copy(), P[b].copy(), z[b].copy()
+    kf._update(xb, Pb, 17, zb, np.ascontiguousarray(R[b]), np.ascontiguousarray(point[b]))
+    assert rel_err(xb, xr[b]) < 1e-9 and rel_err(Pb, Pr[b]) < 1e-7
