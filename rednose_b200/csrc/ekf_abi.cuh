@@ -179,17 +179,12 @@ template <class M, class K>
 inline void batch_maha(HostCtx<M>& ctx, const double* x, const double* P, const double* z, const double* R, const double* ea,
                        long long B, int flags, double* out, void* stream) {
   if (B <= 0) return;
-  static double* scratch = nullptr;
-  static size_t cap = 0;
-  const size_t need = (size_t)B * K::ZDIM * M::EDIM;
-  if (need > cap) {
-    if (scratch) cudaFree(scratch);
-    scratch = nullptr; cap = 0;
-    if (!check(cudaMalloc(&scratch, need * sizeof(double)), "cudaMalloc(maha scratch)")) return;
-    cap = need;
-  }
+  // per-call scratch, allocated and released in stream order (no buffer shared between streams or devices)
+  double* scratch = nullptr;
+  if (!check(cudaMallocAsync((void**)&scratch, sizeof(double) * (size_t)B * K::ZDIM * M::EDIM, (cudaStream_t)stream), "cudaMallocAsync(maha scratch)")) return;
   ekf_maha_thread<M, K><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, P, z, R, ea, B, flags, ctx.gv, out, scratch);
   check(cudaGetLastError(), "ekf_maha launch");
+  check(cudaFreeAsync(scratch, (cudaStream_t)stream), "cudaFreeAsync(maha scratch)");
 }
 
 template <class M>
@@ -220,6 +215,7 @@ inline void host_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, co
   constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM, EA = K::EADIM;
   if (B <= 0) return;
   const long long per = D + E * E + 1 + (long long)n_obs * (Z + Z * Z + EA) + 1;
+  constexpr long long PAD = 8;   // each of the six sub-buffers below is rounded up to an even number of doubles
   long long chunk = (64ll << 20) / (per * 8);  // ~64 MiB of device staging per stream
   if (chunk < 1) chunk = 1;
   if (chunk > B) chunk = B;
@@ -232,13 +228,13 @@ inline void host_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, co
   for (int i = 0; i < NS; ++i)
     if (!streams[i] && !check(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking), "cudaStreamCreate")) return;
   if (!dQ && !check(cudaMalloc(&dQ, sizeof(double) * E * E), "cudaMalloc(Q)")) return;
-  if (chunk * per > dcap) {
+  if (chunk * per + PAD > dcap) {
     for (int i = 0; i < NS; ++i) {
       if (dbuf[i]) cudaFree(dbuf[i]);
       dbuf[i] = nullptr;
-      if (!check(cudaMalloc(&dbuf[i], sizeof(double) * chunk * per), "cudaMalloc(stage)")) return;
+      if (!check(cudaMalloc(&dbuf[i], sizeof(double) * (chunk * per + PAD)), "cudaMalloc(stage)")) return;
     }
-    dcap = chunk * per;
+    dcap = chunk * per + PAD;
   }
   if (!check(cudaMemcpy(dQ, Q, sizeof(double) * E * E, cudaMemcpyHostToDevice), "memcpy Q")) return;
   int si = 0;

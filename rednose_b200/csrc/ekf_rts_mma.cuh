@@ -166,25 +166,28 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp_mma
       M::F_apply(fv, g);   // G[:,lane] = F P_{k|k}[:,lane]
     }
 
-    // ---- P_{k+1|k} = L D L^T (rolled right-looking factorisation, as in ekf_rts_warp) ----
-#pragma unroll 1
+    // ---- P_{k+1|k} = L D L^T, right-looking, FULLY UNROLLED: register arrays are indexed statically, only the rows
+    //      below the pivot are published / updated (231 instead of 484 FMAs), and the reciprocal of the pivot -- the long
+    //      pole of every step -- is started from a register shuffle BEFORE the column makes its round trip through shared
+    //      memory, so the two latencies overlap instead of adding up. ----
+#pragma unroll
     for (int kk = 0; kk < N; ++kk) {
-      if (lane == kk) {
+      const double piv = __shfl_sync(0xffffffffu, A[kk], kk);   // lane kk's diagonal entry is final
+      const double di = 1.0 / piv;
+      if (lane == kk) {   // publish the (unscaled) column below the pivot; rows <= kk of this buffer row are never read
 #pragma unroll
-        for (int i = 0; i < N; ++i) s.LT[kk * LD + i] = A[i];
+        for (int i = kk + 1; i < N; ++i) s.LT[kk * LD + i] = A[i];
       }
-      __syncwarp();
-      const double di = 1.0 / s.LT[kk * LD + kk];
       if (lane == 0) s.dinv[kk] = di;
-      const double cj = s.LT[kk * LD + (act ? lane : 0)] * di;
+      __syncwarp();
+      // L[lane][kk] = c[lane] / D[kk]: read from the published column (not the lane's own A[kk]) so that L is exactly
+      // the factor the substitutions below use; lanes <= kk own finished columns and update nothing
+      const double cj = ((lane > kk && act) ? s.LT[kk * LD + lane] : 0.0) * di;
 #pragma unroll
-      for (int i = 0; i < N; i += 2) {
-        const double2 c2 = *reinterpret_cast<const double2*>(&s.LT[kk * LD + i]);
-        A[i] = fma(-c2.x, cj, A[i]);
-        if (i + 1 < N) A[i + 1] = fma(-c2.y, cj, A[i + 1]);
-      }
+      for (int i = kk + 1; i < N; ++i) A[i] = fma(-s.LT[kk * LD + i], cj, A[i]);
     }
     __syncwarp();
+    // ---- X[:,lane] = (L D L^T)^-1 G[:,lane];  L[i][kk] = LT[kk][i] * dinv[kk] ----
 #pragma unroll
     for (int kk = 0; kk < N; ++kk) {
       const double gk = g[kk] * s.dinv[kk];
@@ -198,10 +201,13 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp_mma
     asm volatile("" : "+l"(LTv));
 #pragma unroll
     for (int kk = N - 2; kk >= 0; --kk) {
-      double acc = 0.0;
+      double acc0 = 0.0, acc1 = 0.0;   // two partial sums: half the dependent-FMA chain of the dot product
 #pragma unroll
-      for (int i = kk + 1; i < N; ++i) acc = fma(LTv[kk * LD + i], g[i], acc);
-      g[kk] = fma(-acc, s.dinv[kk], g[kk]);
+      for (int i = kk + 1; i < N; i += 2) {
+        acc0 = fma(LTv[kk * LD + i], g[i], acc0);
+        if (i + 1 < N) acc1 = fma(LTv[kk * LD + i + 1], g[i + 1], acc1);
+      }
+      g[kk] = fma(-(acc0 + acc1), s.dinv[kk], g[kk]);
       asm volatile("" ::: "memory");
     }
     // g = X[:,lane]

@@ -126,7 +126,7 @@ struct EKFSym {
     std::vector<double> Pn((size_t)dim_err * dim_err);
     for (int i = 0; i < dim_err; ++i)
       for (int j = 0; j < dim_err; ++j) Pn[(size_t)i * dim_err + j] = P[(size_t)src[i] * dim_err + src[j]];
-    P.swap(Pn);
+    std::copy(Pn.begin(), Pn.end(), P.begin());   // into the existing storage: views handed out by P_ptr() stay valid
     if (!augment_times.empty()) {
       augment_times.erase(augment_times.begin());
       augment_times.push_back(filter_time);

@@ -164,9 +164,14 @@ class EKF_sym_pyx(EKF_sym):
 
   def predict_and_update_batch(self, t, kind, z, R, extra_args=[[]], augment=False):  # pylint: disable=dangerous-default-value
     n = len(z)
-    zc = np.ascontiguousarray(np.asarray([np.asarray(zi, dtype=np.float64).reshape(-1) for zi in z], dtype=np.float64).reshape(n, -1))
-    zdim = zc.shape[1] if n else 0
-    Rc = np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(n, zdim, zdim))
+    if n == 0:
+      # an empty observation batch is legal (KalmanFilter.predict_and_observe with no data, ekf_sym.cc:158-194 with n = 0):
+      # predict to t, checkpoint, return the predicted state twice
+      zc, zdim, Rc = np.zeros((0, 1)), 0, np.zeros((0, 1, 1))
+    else:
+      zc = np.ascontiguousarray(np.asarray([np.asarray(zi, dtype=np.float64).reshape(-1) for zi in z], dtype=np.float64).reshape(n, -1))
+      zdim = zc.shape[1]
+      Rc = np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(n, zdim, zdim))
     ea_rows = [np.asarray(extra_args[i] if i < len(extra_args) else [], dtype=np.float64).reshape(-1) for i in range(n)]
     eadim = ea_rows[0].shape[0] if n else 0
     eac = np.ascontiguousarray(np.asarray(ea_rows, dtype=np.float64).reshape(n, eadim)) if eadim else np.zeros(1)

@@ -143,3 +143,33 @@ def test_two_builds_of_one_filter_coexist_per_directory(oracle_dir, tmp_path):
   for kf in (k1, k2):
     kf.predict_and_update_batch(0.1, 1, np.array([[1.2]]), np.array([[[0.01]]]))
   assert np.array_equal(k1.state(), k2.state())
+
+
+def test_empty_observation_batch_predicts_and_checkpoints(oracle_dir):
+  """n = 0 observations (KalmanFilter.predict_and_observe with no data; ekf_sym.cc:158-194 loops zero times):
+  the driver predicts to t, returns the predicted state as both x_{k|k-1} and x_{k|k}, and keeps a checkpoint."""
+  Q, x0, P0 = np.diag([0.01, 4.0]), np.array([0.5, 2.0]), np.eye(2)
+  kf = EKF_sym_pyx(oracle_dir, "kinematic", Q, x0, P0, 2, 2)
+  kf.predict_and_update_batch(1.0, 1, np.array([[0.6]]), np.array([[[0.01]]]))
+  before = kf.state().copy()
+  r = kf.predict_and_update_batch(1.5, 1, [], [])
+  assert r is not None and r[6] == [] and np.array_equal(r[0], r[1]) and np.array_equal(r[2], r[3])
+  assert abs(kf.state()[0] - (before[0] + 0.5 * before[1])) < 1e-12 and kf.get_filter_time() == 1.5
+
+
+def test_covariance_view_survives_augment(oracle_dir):
+  """The .P view points into the driver's storage; augment() (ekf_sym.py:365-391) must rewrite that storage in place."""
+  import os
+  import pytest
+  from oracle import build_ref
+  if not os.path.exists(os.path.join(build_ref.OUT, "libmsckf.so")):
+    pytest.skip("oracle/_ref/libmsckf.so not built")
+  from rednose_b200.filters.msckf import MsckfKalman
+  kf = MsckfKalman(build_ref.OUT).filter
+  rng = np.random.default_rng(0)
+  L = np.tril(rng.normal(size=(82, 82))) * 0.01 + np.eye(82)
+  kf.init_state(MsckfKalman.initial_x, L @ L.T, 0.0)
+  view = kf.P
+  want_new_clone = kf.covs()[:6, :6].copy()
+  kf.augment()
+  assert np.array_equal(view, kf.covs()) and np.array_equal(view[-6:, -6:], want_new_clone)
