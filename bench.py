@@ -659,7 +659,7 @@ def run_msckf(args):
   to_c = torch.as_tensor(to_c_matrix().reshape(9)).to(dev)
   z_host = torch.empty(B, 20, dtype=torch.float64).pin_memory()
   x_host = torch.empty(B, DIM, dtype=torch.float64).pin_memory()
-  stats = {"gated": 0, "tracks": 0}
+  stats = {"gated": 0, "tracks": 0, "bad_triangulations": 0, "count_bad": False}
 
   def make_obs():
     """a new landmark 15-50 m ahead of the newest clone, projected into the 10 clones (+ noise, 5 % gross outliers)"""
@@ -677,6 +677,13 @@ def run_msckf(args):
   def hot_path(z):
     poses = eng.x[:, 23:].contiguous()                     # the 10 clones ARE the poses of the track: [B, 70]
     pos, param, iters = fe.compute_pos_batch(to_c, poses, z)
+    # a track whose triangulation did not converge (gross outliers: Gauss-Newton hits its 30-iteration cap or leaves the
+    # finite range) still goes through the filter, with a finite stand-in point 30 m ahead of the newest clone: its huge
+    # residual is then what the Mahalanobis gate (ekf_c.c:88-94) exists to reject
+    ok = torch.isfinite(pos).all(dim=1) & (iters < 30)
+    stats["bad_triangulations"] += int((~ok).sum()) if stats.get("count_bad") else 0
+    fallback = poses[:, 63:66] + quat2rot_t(poses[:, 66:70])[:, :, 0] * 30.0
+    pos = torch.where(ok[:, None], pos, fallback)
     eng.step(17, dt, z, Rk, ea=pos)                         # the kernel overwrites z with the (projected) innovation
     eng.augment()
     return pos
@@ -699,7 +706,6 @@ def run_msckf(args):
     sync_all()
     for j in range(K):
       z, outl = make_obs()                                  # synthetic camera frame: NOT part of the timed hot path
-      tr_before = torch.einsum('bii->b', eng.P[:, 22:, 22:])
       ev[j][0].record()
       hot_path(z)
       ev[j][1].record()
@@ -713,6 +719,8 @@ def run_msckf(args):
   z, outl = make_obs()
   poses = eng.x[:, 23:].contiguous()
   pos, _, iters = fe.compute_pos_batch(to_c, poses, z)
+  ok = torch.isfinite(pos).all(dim=1) & (iters < 30)
+  pos = torch.where(ok[:, None], pos, poses[:, 63:66] + quat2rot_t(poses[:, 66:70])[:, :, 0] * 30.0)
   maha_before = torch.einsum('bii->b', eng.P[:, 22:, 22:]).clone()
   eng.step(17, dt, z.clone(), Rk, ea=pos)
   gated = (torch.einsum('bii->b', eng.P[:, 22:, 22:]) > maha_before * (1 - 1e-9))
@@ -746,7 +754,7 @@ def run_msckf(args):
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
       "config": {"workload": "msckf_10k", "filter": "msckf", "filters_per_gpu": B, "dim": DIM, "edim": EDIM, "clones": 10, "zdim": 20, "projected_dim": 17,
                  "outlier_fraction": 0.05, "gated_fraction_measured": float(gated.double().mean()), "outliers_among_gated": float((outl & gated).sum() / max(1, int(gated.sum()))),
-                 "gauss_newton_iterations_mean": float(iters.double().mean()),
+                 "gauss_newton_iterations_mean": float(iters.double().mean()), "triangulations_failed_fraction": float((~ok).double().mean()),
                  "l2": f"state {B * EDIM * EDIM * 8 / 2**20:.0f} MiB of P vs 126 MiB of L2: {'larger than L2' if B * EDIM * EDIM * 8 > L2_BYTES else 'FITS in L2'}",
                  "timing": "CUDA events around the hot-path calls of every frame; the synthetic observation generator between frames is excluded",
                  "sharding": "independent filters per GPU, no data-path collective"},

@@ -266,13 +266,13 @@ class BatchedEKF:
       Ps = hist.P_filt if in_place else torch.empty_like(hist.P_filt)
     qi = self._ffi.new("int[]", list(quaternion_idxs) or [0])
     with torch.cuda.device(self.device):
-      if terminal is None:
+      if terminal is None and not k0:
         getattr(self._lib, f"{self.name}_batch_rts")(
           self._cp(hist.x_pred), self._cp(hist.P_pred), self._cp(hist.x_filt), self._cp(hist.P_filt), self._cp(hist.t), 0,
           self._p(xs), self._p(Ps), T, self.B, qi, len(quaternion_idxs) if norm_quats else 0, 1 if norm_quats else 0, self._stream())
       else:
-        xt, Pt = terminal
-        assert xt.is_contiguous() and Pt.is_contiguous() and xt.shape == (self.B, self.dim_x) and Pt.shape == (self.B, self.dim_err, self.dim_err)
+        xt, Pt = terminal if terminal is not None else (None, None)   # the LAST segment of a history has k0 > 0 but no terminal
+        assert xt is None or (xt.is_contiguous() and Pt.is_contiguous() and xt.shape == (self.B, self.dim_x) and Pt.shape == (self.B, self.dim_err, self.dim_err))
         getattr(self._lib, f"{self.name}_batch_rts_segment")(
           self._cp(hist.x_pred), self._cp(hist.P_pred), self._cp(hist.x_filt), self._cp(hist.P_filt), self._cp(hist.t), 0,
           self._p(xs), self._p(Ps), T, self.B, qi, len(quaternion_idxs) if norm_quats else 0, 1 if norm_quats else 0,
