@@ -20,6 +20,7 @@ NORM_AFTER_PREDICT = 1
 NORM_AFTER_UPDATE = 2
 Q_IS_DIAGONAL = 4
 SHARED_R = 8
+AUGMENT = 16   # fused clone-window shift (CTA kernel only)
 
 
 def _as_device(t, device, dtype=torch.float64):
@@ -160,10 +161,15 @@ class BatchedEKF:
     self._check(f"batch_step_{kind}_idx")
     return z
 
-  def step(self, kind, dt, z, R, ea=None, hist_pred=None, hist_filt=None):
-    """Fused predict(dt) + update(kind): one kernel launch, P read and written once."""
+  def step(self, kind, dt, z, R, ea=None, hist_pred=None, hist_filt=None, augment=False):
+    """Fused predict(dt) + update(kind): one kernel launch, P read and written once.  augment=True also shifts the MSCKF
+    clone window (predict_and_update_batch(..., augment=True), ekf_sym.py:527-528): inside the same launch for filters on
+    the CTA-per-filter kernel (EDIM > 32), as a second launch otherwise."""
     keep, dt_ptr, dt_s = self._dt_args(dt)
     z, R, ea, n_obs, flags = self._obs_args(z, R, ea)
+    fused_aug = bool(augment) and self.dim_err > 32
+    if fused_aug:
+      flags |= AUGMENT
     hxp, hPp = (hist_pred if hist_pred is not None else (None, None))
     hxf, hPf = (hist_filt if hist_filt is not None else (None, None))
     with torch.cuda.device(self.device):
@@ -173,17 +179,19 @@ class BatchedEKF:
         self._stream())
     self.launches += 1
     self._check(f"batch_step_{kind}")
+    if augment and not fused_aug:
+      self.augment()
     return z
 
   # driver-style entry point: time in, observations in (host or device), innovations out
-  def predict_and_update_batch(self, t, kind, z, R, extra_args=None):
+  def predict_and_update_batch(self, t, kind, z, R, extra_args=None, augment=False):
     """All B filters observe `kind` at time t (scalar or [B]); returns (x [B,DIM] device, y [B,n,m] device)."""
     if self.filter_time is None:
       self.filter_time = t
     dt = t - self.filter_time
     if not isinstance(dt, torch.Tensor):
       assert dt >= 0
-    y = self.step(kind, dt, z, R, extra_args)
+    y = self.step(kind, dt, z, R, extra_args, augment=augment)
     self.filter_time = t
     return self.x, y
 

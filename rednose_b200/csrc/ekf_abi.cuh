@@ -59,6 +59,11 @@ constexpr int THREAD_MAX_EDIM = 6;
 template <class M, class K, bool PRED, bool UPD>
 inline void launch_step(const StepArgs<M::NG>& a, cudaStream_t st) {
   if (a.B <= 0) return;
+  if ((a.flags & FLAG_AUGMENT) && !(M::EDIM > 32 || K::HAS_HE)) {
+    fprintf(stderr, "[rednose_b200] the fused augment exists only in the CTA-per-filter kernel (EDIM > 32): call <name>_batch_augment\n");
+    last_status() = (int)cudaErrorNotSupported;
+    return;
+  }
   // feature-track kinds (left-null-space projection with He, ekf_c.c:66-76) exist only in the CTA kernel: they go there
   // whatever the state size
   if constexpr (M::EDIM <= THREAD_MAX_EDIM && !K::HAS_HE) {
@@ -180,8 +185,8 @@ inline void batch_maha(HostCtx<M>& ctx, const double* x, const double* P, const 
                        long long B, int flags, double* out, void* stream) {
   if (B <= 0) return;
   // per-call scratch, allocated and released in stream order (no buffer shared between streams or devices)
-  double* scratch = nullptr;
-  if (!check(cudaMallocAsync((void**)&scratch, sizeof(double) * (size_t)B * K::ZDIM * M::EDIM, (cudaStream_t)stream), "cudaMallocAsync(maha scratch)")) return;
+  double* scratch = (double*)stream_alloc(sizeof(double) * (size_t)B * K::ZDIM * M::EDIM, (cudaStream_t)stream, "cudaMallocAsync(maha scratch)");
+  if (!scratch) return;
   ekf_maha_thread<M, K><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, P, z, R, ea, B, flags, ctx.gv, out, scratch);
   check(cudaGetLastError(), "ekf_maha launch");
   check(cudaFreeAsync(scratch, (cudaStream_t)stream), "cudaFreeAsync(maha scratch)");

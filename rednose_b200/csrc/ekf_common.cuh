@@ -22,6 +22,7 @@ enum : int {
   FLAG_NORM_AFTER_UPDATE  = 2,  // ekf_sym.cc:213 / ekf_sym.py:521
   FLAG_Q_DIAG             = 4,  // caller promises Q is diagonal (only its diagonal is read)
   FLAG_SHARED_R           = 8,  // R points at ONE [ZDIM, ZDIM] matrix used by every filter / observation
+  FLAG_AUGMENT            = 16, // MSCKF: shift the clone window after the (last) update, in the same launch (ekf_sym.py:527-528 -> :365-391); CTA kernel only
 };
 
 // One argument block per launch, passed by value (lives in the kernel parameter
@@ -183,6 +184,28 @@ inline bool first_launch_of(const void* kern) {
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lk(mu);
   return configured.insert({dev, kern}).second;
+}
+
+// stream-ordered scratch (cudaMallocAsync).  The default memory pool gives its memory back to the OS at every
+// synchronisation; raising the release threshold once per device keeps it, so a per-call workspace costs microseconds.
+inline void* stream_alloc(size_t bytes, cudaStream_t st, const char* what) {
+  static std::mutex mu;
+  static std::set<int> tuned;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (tuned.insert(dev).second) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+    }
+  }
+  void* p = nullptr;
+  if (!check(cudaMallocAsync(&p, bytes, st), what)) return nullptr;
+  return p;
 }
 
 }  // namespace rnb

@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
   int tj[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) tj[c] = (lane + 32 * c) * (lane + 32 * c + 1) / 2;
+  bool aug = false;   // set below when this launch also shifts the clone window
   auto store_full = [&](double* __restrict__ dst) {
     for (int i = warp; i < E; i += nw) {
       const int ti = i * (i + 1) / 2;
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
     }
     __syncthreads();
     const bool last = (o == a.n_obs - 1);
+    aug = (a.flags & FLAG_AUGMENT) && last && M::EAUG > 0;
     // state injection, normalisation and the small outputs by warp 0 while the other warps start writing P back
     if (tid < 32) {
       M::err_fun(s.x, s.dx, a.gv, s.xo);   // every lane evaluates the small generated function; identical values
@@ -506,9 +508,13 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
       }
       for (int i = tid; i < D; i += 32) {
         const double v = s.xo[i];
-        if (last) a.x[fb * D + i] = v;
+        if (last) {
+          // fused augment (ekf_sym.py:368-370): [main | clone_1 .. clone_N] -> [main | clone_2 .. clone_N | main[:DAUG]]
+          const int si = (!aug || i < M::DMAIN) ? i : (i < D - M::DAUG ? i + M::DAUG : i - (D - M::DAUG));
+          a.x[fb * D + i] = s.xo[si];
+        }
         const_cast<double*>(ws_all)[b * W::SIZE + W::OFF_X + i] = v;  // next observation of this batch starts here
-        if (last && a.hx_filt) a.hx_filt[fb * D + i] = v;
+        if (last && a.hx_filt) a.hx_filt[fb * D + i] = v;              // the history keeps the estimate BEFORE the window shifts (ekf_sym.py:523-528)
       }
       // innovation overwrites z (ekf_c.c:120): the first YDIM entries
       for (int i = tid; i < Y; i += 32) a.z[(b * a.n_obs + o) * Z + i] = s.y[NR + i];
@@ -516,7 +522,21 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
     if (last && a.hP_filt) store_full(a.hP_filt + fb * (long long)(E * E));
   }
 
-  store_full(Pg);
+  if (!aug) {
+    store_full(Pg);
+  } else {
+    // fused augment (ekf_sym.py:372-389): the same selection on rows and columns, src(i) = i for the main block,
+    // i + EAUG for the surviving clones, i - (E - EAUG) (= the first EAUG main error states) for the new clone
+    auto src = [&](int i) { return i < ME ? i : (i < E - M::EAUG ? i + M::EAUG : i - (E - M::EAUG)); };
+    for (int i = warp; i < E; i += nw) {
+      const int sr = src(i);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int j = lane + 32 * c;
+        if (j < E) Pg[i * E + j] = s.Ppk[pk_idx(sr, src(j))];
+      }
+    }
+  }
 }
 
 template <class M, class K, bool PRED, bool UPD>
@@ -524,8 +544,8 @@ inline void launch_step_cta(const StepArgs<M::NG>& a, cudaStream_t st) {
   using W = CtaWs<M, K>;
   // leaf-value workspace of THIS call, allocated and released in stream order (calls on different streams / devices
   // never share it)
-  double* ws = nullptr;
-  if (!check(cudaMallocAsync((void**)&ws, sizeof(double) * (size_t)a.B * W::SIZE, st), "cudaMallocAsync(cta workspace)")) return;
+  double* ws = (double*)stream_alloc(sizeof(double) * (size_t)a.B * W::SIZE, st, "cudaMallocAsync(cta workspace)");
+  if (!ws) return;
   constexpr size_t smem = sizeof(CtaSmem<M, K>);
   if (first_launch_of((const void*)ekf_step_cta<M, K, PRED, UPD>))
     check(cudaFuncSetAttribute(ekf_step_cta<M, K, PRED, UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute");

@@ -93,7 +93,7 @@ constexpr int CP_THREADS = 64;
 
 template <class FM>
 __global__ void __launch_bounds__(CP_THREADS) compute_pos_thread(const double* __restrict__ to_c, const double* __restrict__ poses, const double* __restrict__ img,
-                                                                  double* __restrict__ param, double* __restrict__ pos, int* __restrict__ iters, long long B) {
+                                                                  double* __restrict__ param, double* __restrict__ pos, int* __restrict__ iters, long long B, double fallback_depth) {
   constexpr int K = FM::K, REC = 9 * K, PITCH = REC | 1;
   extern __shared__ double sm[];
   const long long b0 = (long long)blockIdx.x * CP_THREADS;
@@ -112,12 +112,20 @@ __global__ void __launch_bounds__(CP_THREADS) compute_pos_thread(const double* _
   const double* mp = sm + threadIdx.x * PITCH;
   const double* mi = mp + 7 * K;
   double x[3] = {mi[2 * K - 2], mi[2 * K - 1], 0.1};   // compute_pos.c:31-33
-  const int it = gauss_newton_track<FM>(mp, 1, mi, 1, x);
+  int it = gauss_newton_track<FM>(mp, 1, mi, 1, x);
   double p[3];
   double tc[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) tc[i] = __ldg(to_c + i);
   camera_to_ecef(tc, mp + (K - 1) * 7, 1, x, p);
+  // optional guard (fallback_depth > 0; the reference has none): a track whose Gauss-Newton hit the iteration cap or left
+  // the finite range gets a finite stand-in on the optical axis of the last camera and iters = -iterations, so that the
+  // caller / the filter's Mahalanobis gate can reject it instead of a NaN reaching the state
+  if (fallback_depth > 0.0 && (it >= 30 || !(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2])))) {
+    x[0] = 0.0; x[1] = 0.0; x[2] = 1.0 / fallback_depth;
+    camera_to_ecef(tc, mp + (K - 1) * 7, 1, x, p);
+    it = -it;
+  }
   const long long b = b0 + threadIdx.x;
 #pragma unroll
   for (int i = 0; i < 3; ++i) { param[b * 3 + i] = x[i]; pos[b * 3 + i] = p[i]; }
@@ -299,11 +307,11 @@ struct FeatureHost {
 inline FeatureHost& fhost() { static FeatureHost h; return h; }
 
 template <class FM>
-inline void launch_compute_pos(const double* to_c, const double* poses, const double* img, double* param, double* pos, int* iters, long long B, cudaStream_t st) {
+inline void launch_compute_pos(const double* to_c, const double* poses, const double* img, double* param, double* pos, int* iters, long long B, cudaStream_t st, double fallback_depth = 0.0) {
   if (B <= 0) return;
   constexpr size_t smem = sizeof(double) * CP_THREADS * ((9 * FM::K) | 1);
   if (smem > 48 * 1024) cudaFuncSetAttribute(compute_pos_thread<FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  compute_pos_thread<FM><<<(unsigned)((B + CP_THREADS - 1) / CP_THREADS), CP_THREADS, smem, st>>>(to_c, poses, img, param, pos, iters, B);
+  compute_pos_thread<FM><<<(unsigned)((B + CP_THREADS - 1) / CP_THREADS), CP_THREADS, smem, st>>>(to_c, poses, img, param, pos, iters, B, fallback_depth);
   check(cudaGetLastError(), "compute_pos launch");
 }
 
@@ -324,8 +332,8 @@ extern "C" {
 int features_k(void) { return feature_model::K; }
 int features_cuda_status(void) { int s = rnb::last_status(); rnb::last_status() = 0; return s; }
 
-void compute_pos_batch(const double* to_c, const double* poses, const double* img_positions, double* param, double* pos, int* iters, long long B, void* stream) {
-  rnb::launch_compute_pos<feature_model>(to_c, poses, img_positions, param, pos, iters, B, (cudaStream_t)stream);
+void compute_pos_batch(const double* to_c, const double* poses, const double* img_positions, double* param, double* pos, int* iters, long long B, double fallback_depth, void* stream) {
+  rnb::launch_compute_pos<feature_model>(to_c, poses, img_positions, param, pos, iters, B, (cudaStream_t)stream, fallback_depth);
 }
 void merge_features_batch(double* tracks, const double* features, const long long* empty_idxs, int n_features, int n_tracks, long long B, int* fallbacks, void* stream) {
   rnb::launch_merge_features<feature_model>(tracks, features, empty_idxs, n_features, n_tracks, B, fallbacks, (cudaStream_t)stream);

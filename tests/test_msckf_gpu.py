@@ -207,3 +207,30 @@ def test_msckf_feature_kind_single_filter_host_entry_point(msckf_dirs):
     xb, Pb, zb = x[b].copy(), P[b].copy(), z[b].copy()
     kf._update(xb, Pb, 17, zb, np.ascontiguousarray(R[b]), np.ascontiguousarray(point[b]))
     assert rel_err(xb, xr[b]) < 1e-9 and rel_err(Pb, Pr[b]) < 1e-7
+
+
+def test_msckf_fused_augment_equals_step_then_augment(msckf_dirs):
+  """predict_and_update_batch(..., augment=True) (ekf_sym.py:527-528): the clone-window shift done inside the CTA kernel's
+  write-back is the same permutation as the separate <name>_batch_augment launch, bit for bit; the history slabs keep the
+  estimate from before the shift."""
+  gen_dir, oracle_dir = msckf_dirs
+  o = Oracle(oracle_dir, "msckf")
+  B = 37
+  x, P, Q, point = msckf_batch(B, seed=51)
+  z, R, _ = msckf_feature_obs(o, x, point, seed=52, outlier_frac=0.2)
+  e1, e2 = _engine(gen_dir, x, P, Q), _engine(gen_dir, x, P, Q)
+  hx, hP = torch.empty(B, 93, dtype=torch.float64, device="cuda"), torch.empty(B, 82, 82, dtype=torch.float64, device="cuda")
+  e1.step(17, 0.01, z, R, ea=point)
+  pre_x, pre_P = e1.state().copy(), e1.covs().copy()
+  e1.augment()
+  e2.step(17, 0.01, z, R, ea=point, augment=True, hist_filt=(hx, hP))
+  assert np.array_equal(e2.state(), e1.state()) and np.array_equal(e2.covs(), e1.covs())
+  assert np.array_equal(hx.cpu().numpy(), pre_x) and np.array_equal(hP.cpu().numpy(), pre_P)
+  # a plain kind on the big state, two observations per predict: the shift happens once, after the last one
+  ol = Oracle(oracle_dir, "live")
+  z1, R1 = live_obs(ol, 12, x[:, :23], seed=1)
+  z2, R2 = live_obs(ol, 12, x[:, :23], seed=2)
+  e3, e4 = _engine(gen_dir, x, P, Q), _engine(gen_dir, x, P, Q)
+  e3.step(12, 0.02, np.stack([z1, z2], 1), np.stack([R1, R2], 1)); e3.augment()
+  e4.step(12, 0.02, np.stack([z1, z2], 1), np.stack([R1, R2], 1), augment=True)
+  assert np.array_equal(e4.state(), e3.state()) and np.array_equal(e4.covs(), e3.covs())
