@@ -972,7 +972,7 @@ CPU_WHAT = ("reference-generated leaf C (rednose gen_code, unmodified) + Eigen-f
 class CpuArm:
   """The reference's C path (oracle/_ref) on the host cores over a resident batch of filters, stepped in place."""
 
-  def __init__(self, fname, B, nthreads=None, seed=99):
+  def __init__(self, fname, B, nthreads=None, seed=99, pin=True):
     from oracle import build_ref
     from oracle.handle import Arena, Oracle
     if build_ref.reference_available():
@@ -981,7 +981,7 @@ class CpuArm:
     self.o = Oracle(build_ref.OUT, fname)
     x, P, self.Q, self.pools, (self.dim, self.edim), self.quat = _cpu_problem(fname, B, seed)
     self.Q = np.ascontiguousarray(self.Q, dtype=np.float64)
-    self.arena = Arena(self.o, B, nthreads=nthreads)
+    self.arena = Arena(self.o, B, nthreads=nthreads, pin=pin)
     self.arena.load(x, P)             # P [EDIM, EDIM] is broadcast; pages are first-touched by the workers
     self.sched = kind_schedule(fname, 4096)
     self.it = 0
@@ -1042,21 +1042,25 @@ def _cpu_info():
 
 
 def _best_threads(fname):
-  """Thread count for the reference arm: the CPUs the container can actually get, verified by a short sweep (under a
-  CFS quota a few threads fewer than the quota can be faster than the quota itself: any other runnable thread of the
-  container pushes the group over its budget and the whole group is throttled for the rest of the period)."""
+  """(threads, pinned?) for the reference arm: the CPUs the container can actually get, verified by a short sweep.  The
+  GPU boxes are shared and run the container under a CFS quota: a thread count at the quota can be SLOWER than one
+  below it (any other runnable thread of the container pushes the group over its budget and the whole group is
+  throttled for the rest of the period), and pinning to fixed CPUs can land on CPUs other tenants keep busy -- so both
+  are measured, not assumed."""
   n = _threads()
-  cands = sorted({n, max(1, n - 1), max(1, n - 2), max(1, (3 * n) // 4), max(1, n // 2)}, reverse=True)
+  cands = []
+  for c in sorted({n, max(1, n - 1), max(1, n - 2), max(1, (3 * n) // 4)}, reverse=True):
+    cands += [(c, True), (c, False)]
   rates = {}
-  for c in cands:
-    rates[c] = 1.0 / _calibrate(fname, c, n=2048)
+  for c, pin in cands:
+    rates[(c, pin)] = 1.0 / _calibrate(fname, c, n=4096, pin=pin)
   best = max(rates, key=rates.get)
-  return best, {str(k): v for k, v in rates.items()}
+  return best[0], best[1], {f"{c}{'p' if pin else 'u'}": v for (c, pin), v in rates.items()}
 
 
-def _calibrate(fname, nthreads, n=4096):
+def _calibrate(fname, nthreads, n=4096, pin=True):
   """seconds per filter-step with `nthreads` workers (small resident sample, warm)."""
-  arm = CpuArm(fname, n * max(1, nthreads // 4), nthreads=nthreads)
+  arm = CpuArm(fname, n * max(1, nthreads // 4), nthreads=nthreads, pin=pin)
   arm.step()
   t = time.perf_counter()
   for _ in range(3):
@@ -1069,12 +1073,12 @@ def _calibrate(fname, nthreads, n=4096):
 def cpu_reference(fname, workload, budget_s=15.0, steps=None, full_batch=None):
   """cpu_baseline of the GPU line: the reference's C path on all host cores over a bounded resident sample of the
   same workload (same kind schedule), plus one-thread and per-filter-Python-driver figures for context."""
-  cores, sweep = _best_threads(fname)
+  cores, pin, sweep = _best_threads(fname)
   n_steps = steps or 20
-  per = _calibrate(fname, cores)
+  per = _calibrate(fname, cores, pin=pin)
   full = full_batch or WORKLOADS[workload]["batch"]
   Bs = int(max(1024, min(full, budget_s / (per * (n_steps + 2)))))
-  arm = CpuArm(fname, Bs, nthreads=cores)
+  arm = CpuArm(fname, Bs, nthreads=cores, pin=pin)
   arm.step(); arm.step()
   t = time.perf_counter()
   for _ in range(n_steps):
@@ -1110,7 +1114,7 @@ def cpu_reference(fname, workload, budget_s=15.0, steps=None, full_batch=None):
   v = Bs * n_steps / el
   return {"value": v, "unit": "steps/s", "cores": cores, "threads": cores, "threads_pinned": pinned, "kind": "port", **_cpu_info(),
           "one_thread_steps_per_s": one_thread, "thread_scaling_efficiency": v / (cores * one_thread), "copy_bytes_per_step": 0,
-          "thread_sweep_steps_per_s": sweep, "python_driver_per_filter_steps_per_s": py_driver,
+          "thread_sweep_steps_per_s": sweep, "thread_sweep_key": "<threads>p = pinned (spread over the affinity mask), u = unpinned", "python_driver_per_filter_steps_per_s": py_driver,
           "sample": f"{Bs} {fname} filters resident x {n_steps} in-place steps of workload {workload} (same kind schedule), {el:.1f} s",
           "same_batch_as_gpu_arm": Bs == full, "what": CPU_WHAT}
 
@@ -1155,11 +1159,11 @@ def run_reference(args):
     return
   wl = WORKLOADS[args.workload]
   fname, full = wl["filter"], (args.batch or wl["batch"])
-  cores, sweep = _best_threads(fname)
-  per = _calibrate(fname, cores)
+  cores, pin, sweep = _best_threads(fname)
+  per = _calibrate(fname, cores, pin=pin)
   total_budget = 150.0
   Bs = int(max(cores * 8, min(full, total_budget / (args.steps + args.warmup) / per)))
-  arm = CpuArm(fname, Bs, nthreads=cores)
+  arm = CpuArm(fname, Bs, nthreads=cores, pin=pin)
   times = []
   for i in range(args.warmup + args.steps):
     t = time.perf_counter()
@@ -1179,7 +1183,7 @@ def run_reference(args):
   v = Bs / float(np.mean(times))
   cb = {"value": v, "unit": "steps/s", "cores": cores, "threads": cores, "threads_pinned": pinned, "kind": "port", **_cpu_info(),
         "one_thread_steps_per_s": one_thread, "thread_scaling_efficiency": v / (cores * one_thread), "copy_bytes_per_step": 0,
-        "thread_sweep_steps_per_s": sweep, "resident_bytes": resident,
+        "thread_sweep_steps_per_s": sweep, "thread_sweep_key": "<threads>p = pinned (spread over the affinity mask), u = unpinned", "resident_bytes": resident,
         "sample": f"{Bs} {fname} filters resident ({'the full workload batch' if Bs == full else f'of {full}'}), one in-place pass per step, {args.steps} timed steps, workload {args.workload} kind schedule",
         "what": CPU_WHAT}
   line = {"impl": "reference", "metric": "fused EKF predict+update steps/s (batched, float64)", "value": v, "unit": "steps/s",

@@ -229,30 +229,21 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
   //      Warp w takes rows w, w + nw, ...; lanes run along the row (coalesced); RB rows are in flight per round trip. ----
   const int lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
   constexpr int NC = (E + 31) / 32;     // 32-column chunks of a row
-  {
-    constexpr int RB = 9;
-    for (int i0 = warp; i0 < E; i0 += nw * RB) {
-      double v[RB][NC];
+  // cp.async (LDGSTS, 8 bytes per element: a packed row starts 16-byte aligned only every other row): no registers are
+  // held, so the whole triangle is in flight at once -- ONE global round trip, overlapped with the leaf-value loads below
+  // (the register-staged version needed four and spent 23 % of the kernel waiting on them, profiles/r02_cta_ncu_summary.txt)
+  for (int i = warp; i < E; i += nw) {
+    const int ti = i * (i + 1) / 2;
 #pragma unroll
-      for (int rr = 0; rr < RB; ++rr) {
-        const int i = i0 + rr * nw;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const int j = lane + 32 * c;
-          v[rr][c] = (i < E && j <= i) ? Pg[i * E + j] : 0.0;
-        }
-      }
-#pragma unroll
-      for (int rr = 0; rr < RB; ++rr) {
-        const int i = i0 + rr * nw;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const int j = lane + 32 * c;
-          if (i < E && j <= i) s.Ppk[i * (i + 1) / 2 + j] = v[rr][c];
-        }
+    for (int c = 0; c < NC; ++c) {
+      const int j = lane + 32 * c;
+      if (j <= i) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s.Ppk[ti + j]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(Pg + i * E + j) : "memory");
       }
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   // packed -> full row-major matrix in global memory (P itself and the history slabs): coalesced rows, no divisions
   int tj[NC];
 #pragma unroll
@@ -285,6 +276,7 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
     for (int i = tid; i < HL; i += nth) { s.dinv[i] = 0.0; s.yt[i] = 0.0; }
     if (tid == 0) s.gated = 0;
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   // =============================== predict: P <- F P F^T + dt Q (main block) ===============================
@@ -473,11 +465,10 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
       double nd[NKY];   // -1 / D[k] for this lane's k of every k-step
 #pragma unroll
       for (int kq = 0; kq < NKY; ++kq) nd[kq] = -s.dinv[kq * 4 + ft];
-      int tcount = 0, next = warp;   // lower-triangle tiles (mi >= ni) dealt to the warps round-robin
+      // lower-triangle tiles (mi >= ni) dealt to the warps round-robin in packed order: tile t = tri(mi) + ni goes to warp t % NW
+      constexpr int NW = cta_threads<M>() / 32;
       for (int mi = 0; mi < NTE; ++mi)
-      for (int ni = 0; ni <= mi; ++ni, ++tcount) {
-        if (tcount != next) continue;
-        next += nw;
+      for (int ni = ((warp - mi * (mi + 1) / 2) % NW + NW) % NW; ni <= mi; ni += NW) {
         const int r = mi * 8 + fg, c = ni * 8 + 2 * ft, n = ni * 8 + fg;
         const bool ok0 = r < E && c <= r, ok1 = r < E && c + 1 <= r;   // inside the matrix and the lower triangle
         const int p0 = r * (r + 1) / 2 + c;
