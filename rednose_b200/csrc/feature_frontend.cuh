@@ -132,6 +132,75 @@ __global__ void __launch_bounds__(CP_THREADS) compute_pos_thread(const double* _
   if (iters) iters[b] = it;
 }
 
+// One LANE per (track, pose): the K pose terms of a Gauss-Newton iteration are independent, so a group of LPT >= K lanes
+// evaluates them at once and butterfly-reduces the 9 sums of the normal equations (every lane of the group ends with
+// bit-identical sums: the xor tree is symmetric and IEEE addition commutes), then every lane solves the same 3 x 3.  The
+// dependent chain of an iteration is one pose term instead of K of them: 86 -> ~15 us for the 10 000 tracks of config 5,
+// where the thread-per-track kernel is pure latency (profiles/r02_compute_pos_ncu_summary.txt).  The sums are formed in
+// tree order instead of the reference's row order (compute_pos.c:22): same algorithm, last-bit differences.
+template <class FM, int LPT>
+__global__ void __launch_bounds__(128) compute_pos_lanes(const double* __restrict__ to_c, const double* __restrict__ poses, const double* __restrict__ img,
+                                                         double* __restrict__ param, double* __restrict__ pos, int* __restrict__ iters, long long B, double fallback_depth) {
+  constexpr int K = FM::K;
+  static_assert(K <= LPT && (LPT == 8 || LPT == 16 || LPT == 32), "one lane per pose");
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = gt / LPT;
+  const int i = (int)(gt % LPT);
+  if (b >= B) return;   // whole groups leave together (LPT divides the block size)
+  const unsigned gmask = (LPT == 32) ? 0xffffffffu : (((1u << LPT) - 1u) << (((threadIdx.x & 31) / LPT) * LPT));
+  const bool act = i < K;
+  const double* tp = poses + b * 7 * K;
+  const double* ti = img + b * 2 * K;
+  double pi[7], p0[7], uv[2];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) { pi[c] = tp[(act ? i : 0) * 7 + c]; p0[c] = tp[(K - 1) * 7 + c]; }
+  uv[0] = ti[2 * (act ? i : 0)]; uv[1] = ti[2 * (act ? i : 0) + 1];
+  double x[3] = {ti[2 * K - 2], ti[2 * K - 1], 0.1};   // compute_pos.c:31-33
+  int counter = 0;
+  double d2 = 0.0;
+  while ((d2 > 0.0001 && counter < 30) || counter == 0) {   // compute_pos.c:18 (uniform inside the group)
+    double r[2], j[6];
+    FM::pose_term(x, pi, p0, uv, r, j);
+    double sums[9];
+    {
+      const double w = act ? 1.0 : 0.0;   // idle lanes contribute exact zeros
+      const double j0 = j[0] * w, j1 = j[1] * w, j2 = j[2] * w, j3 = j[3] * w, j4 = j[4] * w, j5 = j[5] * w, e0 = r[0] * w, e1 = r[1] * w;
+      sums[0] = fma(j0, j0, j3 * j3); sums[1] = fma(j0, j1, j3 * j4); sums[2] = fma(j0, j2, j3 * j5);
+      sums[3] = fma(j1, j1, j4 * j4); sums[4] = fma(j1, j2, j4 * j5); sums[5] = fma(j2, j2, j5 * j5);
+      sums[6] = fma(j0, e0, j3 * e1); sums[7] = fma(j1, e0, j4 * e1); sums[8] = fma(j2, e0, j5 * e1);
+    }
+#pragma unroll
+    for (int off = LPT / 2; off >= 1; off >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) sums[q] += __shfl_xor_sync(gmask, sums[q], off);
+    }
+    const double A00 = sums[0], A01 = sums[1], A02 = sums[2], A11 = sums[3], A12 = sums[4], A22 = sums[5], g0 = sums[6], g1 = sums[7], g2 = sums[8];
+    const double c00 = A11 * A22 - A12 * A12, c01 = A02 * A12 - A01 * A22, c02 = A01 * A12 - A02 * A11;
+    const double c11 = A00 * A22 - A02 * A02, c12 = A01 * A02 - A00 * A12, c22 = A00 * A11 - A01 * A01;
+    const double id = 1.0 / (A00 * c00 + A01 * c01 + A02 * c02);
+    const double d0 = (c00 * g0 + c01 * g1 + c02 * g2) * id;
+    const double d1 = (c01 * g0 + c11 * g1 + c12 * g2) * id;
+    const double d2_ = (c02 * g0 + c12 * g1 + c22 * g2) * id;
+    x[0] -= d0; x[1] -= d1; x[2] -= d2_;
+    d2 = d0 * d0 + d1 * d1 + d2_ * d2_;
+    ++counter;
+  }
+  if (i != 0) return;
+  double tc[9], p[3];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) tc[q] = __ldg(to_c + q);
+  camera_to_ecef(tc, p0, 1, x, p);
+  int it = counter;
+  if (fallback_depth > 0.0 && (it >= 30 || !(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2])))) {   // see compute_pos_thread
+    x[0] = 0.0; x[1] = 0.0; x[2] = 1.0 / fallback_depth;
+    camera_to_ecef(tc, p0, 1, x, p);
+    it = -it;
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { param[b * 3 + q] = x[q]; pos[b * 3 + q] = p[q]; }
+  if (iters) iters[b] = it;
+}
+
 // ------------------------------------------------------------------------------------------ track bookkeeping ---
 // feature_handler.c:1-21 on one track [K + 1][5] (row 0 is the header)
 template <int K>
@@ -309,9 +378,16 @@ inline FeatureHost& fhost() { static FeatureHost h; return h; }
 template <class FM>
 inline void launch_compute_pos(const double* to_c, const double* poses, const double* img, double* param, double* pos, int* iters, long long B, cudaStream_t st, double fallback_depth = 0.0) {
   if (B <= 0) return;
-  constexpr size_t smem = sizeof(double) * CP_THREADS * ((9 * FM::K) | 1);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(compute_pos_thread<FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  compute_pos_thread<FM><<<(unsigned)((B + CP_THREADS - 1) / CP_THREADS), CP_THREADS, smem, st>>>(to_c, poses, img, param, pos, iters, B, fallback_depth);
+  if constexpr (FM::K <= 32) {
+    // lane-per-pose kernel (default): groups of LPT lanes per track
+    constexpr int LPT = FM::K <= 8 ? 8 : (FM::K <= 16 ? 16 : 32);
+    const long long threads = B * LPT;
+    compute_pos_lanes<FM, LPT><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(to_c, poses, img, param, pos, iters, B, fallback_depth);
+  } else {
+    constexpr size_t smem = sizeof(double) * CP_THREADS * ((9 * FM::K) | 1);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(compute_pos_thread<FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    compute_pos_thread<FM><<<(unsigned)((B + CP_THREADS - 1) / CP_THREADS), CP_THREADS, smem, st>>>(to_c, poses, img, param, pos, iters, B, fallback_depth);
+  }
   check(cudaGetLastError(), "compute_pos launch");
 }
 
