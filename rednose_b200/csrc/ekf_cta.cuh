@@ -407,13 +407,15 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
         for (int i = 0; i < Y; ++i) A[i] = (K::MAHA && pass == 1) ? A1[K::MAHA ? i : 0] : A0[i];
 #pragma unroll
         for (int kk = 0; kk < Y; ++kk) {
+          // the pivot's reciprocal (the long pole of a step) starts from a register shuffle, before the column's round
+          // trip through shared memory
+          const double di = 1.0 / __shfl_sync(0xffffffffu, A[kk], kk);
           if (tid == kk) {   // lane kk publishes its (unscaled) column: rows kk .. Y-1
 #pragma unroll
             for (int i = kk; i < Y; ++i) LT[kk * SL + i] = A[i];
+            s.dinv[kk] = di;
           }
           __syncwarp();
-          const double di = 1.0 / LT[kk * SL + kk];
-          if (tid == 0) s.dinv[kk] = di;
           // L[lane][kk] = c[lane] / D[kk] (symmetry: c[lane] is the lane's own A[kk]); the y lane uses its own entry
           const double cj = ((tid == Y) ? A[kk] : LT[kk * SL + j]) * di;
 #pragma unroll
