@@ -338,6 +338,28 @@ def run_gpu(args):
     except Exception as ex:  # pylint: disable=broad-except
       host_abi = {"error": repr(ex)[:200]}
 
+  # ---- the reference's own calling pattern: ONE filter, host arrays, <name>_predict + <name>_update_<k> per call through the
+  #      Python driver (BASELINE config 1 is this plumbing; the number says what a user who does NOT batch pays per call) ----
+  single = None
+  if rank == 0:
+    try:
+      from rednose_b200.ekf_sym import EKF_sym
+      kf1 = EKF_sym(lib_dir, fname, Q, x0[0], P0 if P0.ndim == 2 else P0[0], dim, edim, quaternion_idxs=quat)
+      k1 = sched[args.warmup + 1]
+      z1, R1 = pools[k1][0][0][:1], pools[k1][1][:1]
+      tt = 0.0
+      for _ in range(20):
+        tt += 0.01; kf1.predict_and_update_batch(tt, k1, z1, R1)
+      n1 = 300
+      t_s = time.perf_counter()
+      for _ in range(n1):
+        tt += 0.01; kf1.predict_and_update_batch(tt, k1, z1, R1)
+      dt1 = (time.perf_counter() - t_s) / n1
+      single = {"us_per_predict_and_update_batch": dt1 * 1e6, "steps_per_s": 1.0 / dt1, "kind": k1,
+                "what": f"EKF_sym.predict_and_update_batch on ONE filter with host arrays: {fname}_predict + {fname}_update_{k1} through the C-ABI, each = one pinned staging copy in, a B = 1 launch, one copy out (cpu_baseline.python_driver_per_filter_steps_per_s is the same call pattern on the CPU library)"}
+    except Exception as ex:  # pylint: disable=broad-except
+      single = {"error": repr(ex)[:200]}
+
   # ---- final gather of the state estimates (the only collective of the system) ----
   gather_ms = None
   if world > 1:
@@ -408,6 +430,8 @@ def run_gpu(args):
       line["e2e_pose_columns_only"] = e2e_pose
     if host_abi is not None:
       line["e2e_stateless_host_c_abi"] = host_abi
+    if single is not None:
+      line["single_filter_dropin"] = single
     if gather_ms is not None:
       line["final_gather_ms"] = gather_ms
       line["final_gather_P_ms"] = gather_P_ms

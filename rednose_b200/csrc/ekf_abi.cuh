@@ -41,7 +41,23 @@ struct HostCtx {
   std::mutex mu;
   double* d_scratch = nullptr;
   size_t scratch_doubles = 0;
+  double* h_pinned = nullptr;      // pinned host staging of the single-filter entry points: one copy in, one copy out
+  size_t pinned_doubles = 0;
   cudaStream_t stream = nullptr;
+
+  double* pinned(size_t n) {
+    if (n > pinned_doubles) {
+      if (h_pinned) cudaFreeHost(h_pinned);
+      h_pinned = nullptr; pinned_doubles = 0;
+      if (!check(cudaMallocHost((void**)&h_pinned, n * sizeof(double)), "cudaMallocHost(staging)")) return nullptr;
+      pinned_doubles = n;
+    }
+    return h_pinned;
+  }
+  cudaStream_t single_stream() {
+    if (!stream) check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate(single)");
+    return stream;
+  }
 
   double* scratch(size_t n) {
     if (n > scratch_doubles) {
@@ -273,23 +289,28 @@ inline void host_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, co
 }
 
 // --------------------------------------------- single filter, HOST pointers ---
+// The reference's own entry points (<name>_predict / <name>_update_<kind> on caller-owned host arrays, one filter).  All
+// inputs are packed into ONE pinned staging buffer and travel in one asynchronous copy each way on a private stream
+// (round 1 issued 3-5 synchronous pageable cudaMemcpy per direction): copy in, launch with B = 1, copy out, one wait.
 template <class M>
 inline void single_predict(HostCtx<M>& ctx, double* x, double* P, const double* Q, double dt) {
   constexpr int D = M::DIM, E = M::EDIM;
   std::lock_guard<std::mutex> lk(ctx.mu);
   constexpr int DA = (D + 1) & ~1;   // P starts 16-byte aligned behind x (covariance tiles move by bulk copy / 128-bit accesses)
-  double* d = ctx.scratch(DA + 2 * E * E);
-  if (!d) return;
-  double* dx = d; double* dP = d + DA; double* dQ = dP + E * E;
-  if (!check(cudaMemcpy(dx, x, sizeof(double) * D, cudaMemcpyHostToDevice), "memcpy x")) return;
-  cudaMemcpy(dP, P, sizeof(double) * E * E, cudaMemcpyHostToDevice);
-  cudaMemcpy(dQ, Q, sizeof(double) * E * E, cudaMemcpyHostToDevice);
+  constexpr size_t N = DA + 2 * E * E;
+  double* d = ctx.scratch(N);
+  double* h = ctx.pinned(N);
+  cudaStream_t st = ctx.single_stream();
+  if (!d || !h || !st) return;
+  memcpy(h, x, sizeof(double) * D); memcpy(h + DA, P, sizeof(double) * E * E); memcpy(h + DA + E * E, Q, sizeof(double) * E * E);
+  if (!check(cudaMemcpyAsync(d, h, sizeof(double) * N, cudaMemcpyHostToDevice, st), "memcpy in")) return;
   StepArgs<M::NG> a;
   fill_common<M>(a, ctx, 1, nullptr, 0, 0);
-  a.x = dx; a.P = dP; a.Q = dQ; a.dt = dt;
-  launch_step<M, NullKind, true, false>(a, nullptr);
-  cudaMemcpy(x, dx, sizeof(double) * D, cudaMemcpyDeviceToHost);
-  check(cudaMemcpy(P, dP, sizeof(double) * E * E, cudaMemcpyDeviceToHost), "memcpy P back");
+  a.x = d; a.P = d + DA; a.Q = d + DA + E * E; a.dt = dt;
+  launch_step<M, NullKind, true, false>(a, st);
+  cudaMemcpyAsync(h, d, sizeof(double) * (DA + E * E), cudaMemcpyDeviceToHost, st);
+  if (!check(cudaStreamSynchronize(st), "single_predict")) return;
+  memcpy(x, h, sizeof(double) * D); memcpy(P, h + DA, sizeof(double) * E * E);
 }
 
 template <class M, class K>
@@ -297,22 +318,24 @@ inline void single_update(HostCtx<M>& ctx, double* x, double* P, double* z, cons
   constexpr int D = M::DIM, E = M::EDIM, Z = K::ZDIM, EA = K::EADIM;
   std::lock_guard<std::mutex> lk(ctx.mu);
   constexpr int DA = (D + 1) & ~1;   // see single_predict
-  double* d = ctx.scratch(DA + E * E + Z + Z * Z + (EA > 0 ? EA : 1));
-  if (!d) return;
-  double* dx = d; double* dP = d + DA; double* dz = dP + E * E; double* dR = dz + Z; double* dea = dR + Z * Z;
-  if (!check(cudaMemcpy(dx, x, sizeof(double) * D, cudaMemcpyHostToDevice), "memcpy x")) return;
-  cudaMemcpy(dP, P, sizeof(double) * E * E, cudaMemcpyHostToDevice);
-  cudaMemcpy(dz, z, sizeof(double) * Z, cudaMemcpyHostToDevice);
-  cudaMemcpy(dR, R, sizeof(double) * Z * Z, cudaMemcpyHostToDevice);
-  if (EA > 0 && ea) cudaMemcpy(dea, ea, sizeof(double) * EA, cudaMemcpyHostToDevice);
+  constexpr size_t OZ = DA + E * E, OR_ = OZ + Z, OEA = OR_ + Z * Z, N = OEA + (EA > 0 ? EA : 1);
+  double* d = ctx.scratch(N);
+  double* h = ctx.pinned(N);
+  cudaStream_t st = ctx.single_stream();
+  if (!d || !h || !st) return;
+  memcpy(h, x, sizeof(double) * D); memcpy(h + DA, P, sizeof(double) * E * E); memcpy(h + OZ, z, sizeof(double) * Z);
+  memcpy(h + OR_, R, sizeof(double) * Z * Z);
+  if (EA > 0 && ea) memcpy(h + OEA, ea, sizeof(double) * EA);
+  if (!check(cudaMemcpyAsync(d, h, sizeof(double) * N, cudaMemcpyHostToDevice, st), "memcpy in")) return;
   StepArgs<M::NG> a;
   fill_common<M>(a, ctx, 1, nullptr, 0, 0);
-  a.x = dx; a.P = dP; a.z = dz; a.R = dR; a.ea = (EA > 0 && ea) ? dea : nullptr; a.ea_dim = EA;
-  launch_step<M, K, false, true>(a, nullptr);
-  cudaMemcpy(x, dx, sizeof(double) * D, cudaMemcpyDeviceToHost);
-  cudaMemcpy(P, dP, sizeof(double) * E * E, cudaMemcpyDeviceToHost);
+  a.x = d; a.P = d + DA; a.z = d + OZ; a.R = d + OR_; a.ea = (EA > 0 && ea) ? d + OEA : nullptr; a.ea_dim = EA;
+  launch_step<M, K, false, true>(a, st);
+  cudaMemcpyAsync(h, d, sizeof(double) * (OZ + Z), cudaMemcpyDeviceToHost, st);
+  if (!check(cudaStreamSynchronize(st), "single_update")) return;
+  memcpy(x, h, sizeof(double) * D); memcpy(P, h + DA, sizeof(double) * E * E);
   // ekf_c.c:120: the innovation overwrites z (K::YDIM entries: ZDIM, or ZDIM-EADIM after projection)
-  check(cudaMemcpy(z, dz, sizeof(double) * K::YDIM, cudaMemcpyDeviceToHost), "memcpy y back");
+  memcpy(z, h + OZ, sizeof(double) * K::YDIM);
 }
 
 // leaf functions exported with host pointers (ekf_sym.py:155-161): one-thread kernels
