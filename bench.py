@@ -975,9 +975,8 @@ def run_extras(dev, peak):
     zp = torch.as_tensor(hz[None, :] + rng.normal(0, 1e-3, (B, 20))).to(dev)
     Rk = torch.as_tensor(np.eye(20) * 1e-6).to(dev)
     ea = torch.as_tensor(np.tile(point, (B, 1))).to(dev)
-    def mstep():   # one camera frame: fused predict + gated feature update, then the clone window shifts (augment=True)
-      e.step(17, 0.01, zp.clone(), Rk, ea=ea)
-      e.augment()
+    def mstep():   # one camera frame: fused predict + gated feature update + clone-window shift (augment=True) in one launch pair
+      e.step(17, 0.01, zp.clone(), Rk, ea=ea, augment=True)
     ms = _time_ms(mstep, 10, torch, dev)
     bs = 8 * (2 * EDIM * EDIM + 2 * DIM + 20 + 400 + 17 + 3 + 1)
     out["msckf_10k_feature_step"] = {"filters": B, "ms_per_step": ms, "steps_per_s": B / (ms * 1e-3), "GBps_algorithmic": bs * B / (ms * 1e-3) / 1e9,
