@@ -522,14 +522,27 @@ def run_rts(args):
   tile = min(cs.tile_size(T), B)
   # smoothed pose columns go back to pinned host memory, segment by segment (the result a caller keeps; P stays on the device)
   pose_cols = 7
-  host_out = torch.empty(min(S + 1, T), tile, pose_cols, dtype=torch.float64).pin_memory()
-  stage = torch.empty(min(S + 1, T), tile, pose_cols, dtype=torch.float64, device=dev)
-  chk = {"finite": True, "n": 0}
+  # two slots: the device-to-host copy of one segment's poses runs on a side stream under the next segment's kernels
+  host_out = [torch.empty(min(S + 1, T), tile, pose_cols, dtype=torch.float64).pin_memory() for _ in range(2)]
+  stage = [torch.empty(min(S + 1, T), tile, pose_cols, dtype=torch.float64, device=dev) for _ in range(2)]
+  s_out = torch.cuda.Stream(dev)
+  ev_ready = [torch.cuda.Event() for _ in range(2)]
+  ev_done = [torch.cuda.Event() for _ in range(2)]
+  chk = {"finite": True, "n": 0, "k": 0}
 
   def sink(lo, hi, k0, xs, Ps):
     n = xs.shape[0]
-    stage[:n, :hi - lo].copy_(xs[:, :, :pose_cols])
-    host_out[:n, :hi - lo].copy_(stage[:n, :hi - lo], non_blocking=True)
+    slot = chk["k"] % 2
+    main = torch.cuda.current_stream(dev)
+    if chk["k"] >= 2:
+      main.wait_event(ev_done[slot])                     # the slot's previous copy has left the device
+    stage[slot][:n, :hi - lo].copy_(xs[:, :, :pose_cols])
+    ev_ready[slot].record(main)
+    s_out.wait_event(ev_ready[slot])
+    with torch.cuda.stream(s_out):
+      host_out[slot][:n, :hi - lo].copy_(stage[slot][:n, :hi - lo], non_blocking=True)
+      ev_done[slot].record(s_out)
+    chk["k"] += 1
     counters["d2h"] += n * (hi - lo) * pose_cols * 8
     chk["n"] += n * (hi - lo)
     if k0 == 0:
@@ -558,6 +571,7 @@ def run_rts(args):
       cs.run(x0d, P0d, T, obs_fn, sink, norm_quats=True)
       for k_ in acc:
         acc[k_] += cs.stats[k_]
+    torch.cuda.current_stream(dev).wait_stream(s_out)   # the last poses are in host memory before the clock stops
     t1.record()
     sync_all()
   elapsed_ms, fwd_ms, refwd_ms, bwd_ms = _max_over_ranks(torch, dist, world, dev, [t0.elapsed_time(t1), acc["forward_ms"], acc["reforward_with_history_ms"], acc["backward_ms"]])
