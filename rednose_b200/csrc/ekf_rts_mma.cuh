@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(RTS_WARPS * 32, RTS_MIN_CTAS) ekf_rts_warp_mma
       if (lane == kk) {   // publish the (unscaled) column below the pivot; rows <= kk of this buffer row are never read
 #pragma unroll
         for (int i = kk + 1; i < N; ++i) s.LT[kk * LD + i] = A[i];
+        s.dinv[kk] = di;
       }
-      if (lane == 0) s.dinv[kk] = di;
       __syncwarp();
       // L[lane][kk] = c[lane] / D[kk]: read from the published column (not the lane's own A[kk]) so that L is exactly
       // the factor the substitutions below use; lanes <= kk own finished columns and update nothing
