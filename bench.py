@@ -507,16 +507,42 @@ def run_rts(args):
   # observations in pinned HOST memory (two realisations per kind), copied to the device inside the timed region every step
   hz = {k: [torch.as_tensor(np.ascontiguousarray(z[j])).pin_memory() for j in range(z.shape[0])] for k, (z, _) in pools.items()}
   Rk = {k: torch.as_tensor(R[0]).to(dev) for k, (_, R) in pools.items()}
-  zdev = torch.empty(B, 3, dtype=torch.float64, device=dev)
   sched = kind_schedule("live", T)
   counters = {"h2d": 0, "d2h": 0}
+  # observations: pinned host -> device on a copy stream, one step ahead of the kernels (two device slots), so the 3 MB
+  # per step ride under the previous step's kernel instead of in front of it (same idea as streaming.HostStreamer)
+  zslot = [torch.empty(B, 3, dtype=torch.float64, device=dev) for _ in range(2)]
+  s_in = torch.cuda.Stream(dev)
+  ev_in = [torch.cuda.Event() for _ in range(2)]
+  ev_used = [torch.cuda.Event() for _ in range(2)]
+  pre = {"k": None, "n": 0}
 
-  def obs_fn(k, lo, hi):
+  def _enqueue(k, lo, hi, slot, wait_used):
     kind = sched[k]
     src = hz[kind][k % len(hz[kind])]
-    zdev[lo:hi].copy_(src[lo:hi], non_blocking=True)
+    if wait_used:
+      s_in.wait_event(ev_used[slot])                  # the kernel that last used this slot has been enqueued and finished
+    with torch.cuda.stream(s_in):
+      zslot[slot][lo:hi].copy_(src[lo:hi], non_blocking=True)
+      ev_in[slot].record(s_in)
     counters["h2d"] += (hi - lo) * 3 * 8
-    return 0.01 * (k + 1), kind, zdev[lo:hi], Rk[kind]
+
+  def obs_fn(k, lo, hi):
+    main = torch.cuda.current_stream(dev)
+    n = pre["n"]
+    if n:
+      ev_used[(n - 1) % 2].record(main)               # everything enqueued so far (incl. the previous step) precedes this point
+    slot = n % 2
+    if pre["k"] != (k, lo, hi):                       # not prefetched (first step of a pass / segment)
+      _enqueue(k, lo, hi, slot, n >= 2)
+    main.wait_event(ev_in[slot])
+    if k + 1 < T:
+      _enqueue(k + 1, lo, hi, (n + 1) % 2, n >= 1)
+      pre["k"] = (k + 1, lo, hi)
+    else:
+      pre["k"] = None
+    pre["n"] = n + 1
+    return 0.01 * (k + 1), sched[k], zslot[slot][lo:hi], Rk[sched[k]]
 
   cs = CheckpointedSmoother(d, "live", Q, dim, edim, quaternion_idxs=quat, device=dev, hbm_budget_bytes=int(args.hbm_budget_gb) << 30, segment=S)
   tile = min(cs.tile_size(T), B)
