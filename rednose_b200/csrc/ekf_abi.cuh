@@ -35,38 +35,48 @@ struct GV { double v[NG > 0 ? NG : 1]; };
 // Per-library host context: global_vars (ekf_sym.py:129-132 keeps them as file
 // statics; here they are copied into every launch's argument block) and a small
 // device scratch used by the single-filter host-pointer entry points.
+constexpr int MAX_DEVICES = 32;
+inline int current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < MAX_DEVICES) ? d : 0; }
+
 template <class M>
 struct HostCtx {
   GV<M::NG> gv{};
   std::mutex mu;
-  double* d_scratch = nullptr;
-  size_t scratch_doubles = 0;
-  double* h_pinned = nullptr;      // pinned host staging of the single-filter entry points: one copy in, one copy out
-  size_t pinned_doubles = 0;
-  cudaStream_t stream = nullptr;
-
-  double* pinned(size_t n) {
-    if (n > pinned_doubles) {
-      if (h_pinned) cudaFreeHost(h_pinned);
-      h_pinned = nullptr; pinned_doubles = 0;
-      if (!check(cudaMallocHost((void**)&h_pinned, n * sizeof(double)), "cudaMallocHost(staging)")) return nullptr;
-      pinned_doubles = n;
-    }
-    return h_pinned;
-  }
-  cudaStream_t single_stream() {
-    if (!stream) check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate(single)");
-    return stream;
-  }
+  // device scratch / pinned staging / private stream of the single-filter entry points, ONE SET PER DEVICE (a process may
+  // drive several GPUs; a pointer or stream created on device 0 must never be used while device 1 is current)
+  struct PerDevice {
+    double* d_scratch = nullptr;
+    size_t scratch_doubles = 0;
+    double* h_pinned = nullptr;      // pinned host staging: one copy in, one copy out
+    size_t pinned_doubles = 0;
+    cudaStream_t stream = nullptr;
+  };
+  PerDevice dev[MAX_DEVICES];
 
   double* scratch(size_t n) {
-    if (n > scratch_doubles) {
-      if (d_scratch) cudaFree(d_scratch);
-      d_scratch = nullptr; scratch_doubles = 0;
-      if (!check(cudaMalloc(&d_scratch, n * sizeof(double)), "cudaMalloc(scratch)")) return nullptr;
-      scratch_doubles = n;
+    PerDevice& p = dev[current_device()];
+    if (n > p.scratch_doubles) {
+      if (p.d_scratch) cudaFree(p.d_scratch);
+      p.d_scratch = nullptr; p.scratch_doubles = 0;
+      if (!check(cudaMalloc(&p.d_scratch, n * sizeof(double)), "cudaMalloc(scratch)")) return nullptr;
+      p.scratch_doubles = n;
     }
-    return d_scratch;
+    return p.d_scratch;
+  }
+  double* pinned(size_t n) {
+    PerDevice& p = dev[current_device()];
+    if (n > p.pinned_doubles) {
+      if (p.h_pinned) cudaFreeHost(p.h_pinned);
+      p.h_pinned = nullptr; p.pinned_doubles = 0;
+      if (!check(cudaMallocHost((void**)&p.h_pinned, n * sizeof(double)), "cudaMallocHost(staging)")) return nullptr;
+      p.pinned_doubles = n;
+    }
+    return p.h_pinned;
+  }
+  cudaStream_t single_stream() {
+    PerDevice& p = dev[current_device()];
+    if (!p.stream) check(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking), "cudaStreamCreate(single)");
+    return p.stream;
   }
 };
 
@@ -241,11 +251,14 @@ inline void host_step(HostCtx<M>& ctx, double* x, double* P, const double* Q, co
   if (chunk < 1) chunk = 1;
   if (chunk > B) chunk = B;
   constexpr int NS = 3;
-  static cudaStream_t streams[NS] = {nullptr, nullptr, nullptr};
-  static double* dbuf[NS] = {nullptr, nullptr, nullptr};
-  static long long dcap = 0;
-  static double* dQ = nullptr;
+  struct Stage { cudaStream_t streams[NS] = {nullptr, nullptr, nullptr}; double* dbuf[NS] = {nullptr, nullptr, nullptr}; long long dcap = 0; double* dQ = nullptr; };
+  static Stage stages[MAX_DEVICES];   // streams and staging buffers belong to the device that is current
   std::lock_guard<std::mutex> lk(ctx.mu);
+  Stage& sg = stages[current_device()];
+  cudaStream_t* streams = sg.streams;
+  double** dbuf = sg.dbuf;
+  long long& dcap = sg.dcap;
+  double*& dQ = sg.dQ;
   for (int i = 0; i < NS; ++i)
     if (!streams[i] && !check(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking), "cudaStreamCreate")) return;
   if (!dQ && !check(cudaMalloc(&dQ, sizeof(double) * E * E), "cudaMalloc(Q)")) return;

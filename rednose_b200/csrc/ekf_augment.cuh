@@ -34,11 +34,8 @@ template <class M>
 inline void launch_augment(double* x, double* P, long long B, int dim_augment, int dim_augment_err, cudaStream_t st) {
   if (B <= 0) return;
   const size_t smem = sizeof(double) * (M::EDIM * M::EDIM + M::DIM);
-  static bool configured = false;
-  if (!configured) {
+  if (first_launch_of((const void*)ekf_augment_cta<M>))   // per (device, kernel)
     cudaFuncSetAttribute(ekf_augment_cta<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
   ekf_augment_cta<M><<<(unsigned)B, 128, smem, st>>>(x, P, B, dim_augment, dim_augment_err);
   check(cudaGetLastError(), "ekf_augment launch");
 }

@@ -361,16 +361,17 @@ __global__ void res_jac_kernel(const double* x, const double* poses, const doubl
 // ------------------------------------------------------------------------------------------------- host side ---
 struct FeatureHost {
   std::mutex mu;
-  double* d = nullptr; size_t cap = 0;          // device scratch of the single-instance entry points
-  bool cp_configured = false, mf_configured = false;
+  // device scratch of the single-instance entry points, one per device
+  double* d[32] = {nullptr}; size_t cap[32] = {0};
   double* scratch(size_t bytes) {
-    if (bytes > cap) {
-      if (d) cudaFree(d);
-      d = nullptr; cap = 0;
-      if (!check(cudaMalloc(&d, bytes), "cudaMalloc(feature scratch)")) return nullptr;
-      cap = bytes;
+    int dev = 0; cudaGetDevice(&dev); if (dev < 0 || dev >= 32) dev = 0;
+    if (bytes > cap[dev]) {
+      if (d[dev]) cudaFree(d[dev]);
+      d[dev] = nullptr; cap[dev] = 0;
+      if (!check(cudaMalloc(&d[dev], bytes), "cudaMalloc(feature scratch)")) return nullptr;
+      cap[dev] = bytes;
     }
-    return d;
+    return d[dev];
   }
 };
 inline FeatureHost& fhost() { static FeatureHost h; return h; }
