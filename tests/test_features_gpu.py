@@ -88,3 +88,25 @@ def test_sane_batch(fe):
   got = fe.sane_batch(torch.as_tensor(tracks).cuda()).cpu().numpy()
   want = np.array([py_sane(t) for t in tracks]).astype(np.int32)
   assert np.array_equal(got, want) and 0 < want.sum() < 5000
+
+
+def test_compute_pos_fallback_guard(fe):
+  """fallback_depth > 0 (an addition; the reference has no guard): a track whose Gauss-Newton does not converge comes back
+  finite, on the last camera's optical axis, flagged by a negative iteration count; converged tracks are untouched."""
+  import torch
+  from rednose_b200.geometry import quat2rot
+  to_c, poses, img, _ = synth_tracks(500, seed=21, noise=1e-3)
+  img_bad = img.copy()
+  bad = np.arange(0, 500, 25)
+  rng = np.random.default_rng(3)
+  img_bad[bad] = rng.normal(0, 5.0, (bad.size, 2 * K))          # observations unrelated to the geometry
+  p0, _, it0 = fe.compute_pos_batch(to_c, torch.as_tensor(poses).cuda(), torch.as_tensor(img_bad).cuda())
+  p1, _, it1 = fe.compute_pos_batch(to_c, torch.as_tensor(poses).cuda(), torch.as_tensor(img_bad).cuda(), fallback_depth=30.0)
+  p0, p1, it0, it1 = p0.cpu().numpy(), p1.cpu().numpy(), it0.cpu().numpy(), it1.cpu().numpy()
+  failed = (it0 >= 30) | ~np.isfinite(p0).all(axis=1)
+  assert failed.any() and set(np.nonzero(failed)[0]) <= set(bad)
+  assert np.isfinite(p1).all() and np.array_equal(it1 < 0, failed) and np.array_equal(p1[~failed], p0[~failed])
+  P = poses.reshape(500, K, 7)
+  for b in np.nonzero(failed)[0]:
+    want = P[b, K - 1, 0:3] + quat2rot(P[b, K - 1, 3:7]) @ to_c.T @ np.array([0.0, 0.0, 30.0])
+    assert np.max(np.abs(p1[b] - want)) < 1e-6
