@@ -75,7 +75,10 @@ class RewindingScheduler(RaggedScheduler):
   per kind).  No new kernel: the ring is plumbing around `<name>_batch_step_<kind>_idx`.
   """
 
-  def __init__(self, engine, zdims, depth=16, max_rewind_age=1.0, ea_dims=None):
+  def __init__(self, engine, zdims, depth=16, max_rewind_age=1.0, ea_dims=None, packed=False):
+    """packed=True stores the covariance snapshots as their lower triangle (EDIM (EDIM + 1) / 2 doubles instead of EDIM^2:
+    half the ring -- the reference's 512-deep ring then fits 100 000 live filters in one B200's HBM); a restored covariance
+    is then exactly symmetric (upper := lower), which differs from the stored one by the kernels' last-bit asymmetry."""
     super().__init__(engine)
     B, dev = engine.B, engine.device
     self.N, self.max_rewind_age = int(depth), float(max_rewind_age)
@@ -85,7 +88,17 @@ class RewindingScheduler(RaggedScheduler):
     f64 = dict(dtype=torch.float64, device=dev)
     self.ring_t = torch.full((B, self.N), float("nan"), **f64)
     self.ring_x = torch.zeros(B, self.N, engine.x.shape[1], **f64)
-    self.ring_P = torch.zeros(B, self.N, engine.P.shape[1], engine.P.shape[2], **f64)
+    E = engine.P.shape[1]
+    self.packed = bool(packed)
+    if self.packed:
+      tr = torch.tril_indices(E, E, device=dev)
+      self._tri_r, self._tri_c = tr[0], tr[1]
+      ii, jj = torch.meshgrid(torch.arange(E, device=dev), torch.arange(E, device=dev), indexing="ij")
+      hi, lo = torch.maximum(ii, jj), torch.minimum(ii, jj)
+      self._unpack = (hi * (hi + 1) // 2 + lo).reshape(-1)      # full (i, j) -> packed index of (max, min)
+      self.ring_P = torch.zeros(B, self.N, E * (E + 1) // 2, **f64)
+    else:
+      self.ring_P = torch.zeros(B, self.N, E, E, **f64)
     self.ring_kind = torch.zeros(B, self.N, dtype=torch.int64, device=dev)
     self.ring_z = torch.zeros(B, self.N, zmax, **f64)
     self.ring_R = torch.zeros(B, self.N, zmax, zmax, **f64)
@@ -103,7 +116,7 @@ class RewindingScheduler(RaggedScheduler):
     m = z.shape[-1]
     self.ring_t[ids, pos] = t
     self.ring_x[ids, pos] = self.e.x[ids]
-    self.ring_P[ids, pos] = self.e.P[ids]
+    self.ring_P[ids, pos] = self.e.P[ids][:, self._tri_r, self._tri_c] if self.packed else self.e.P[ids]
     self.ring_kind[ids, pos] = kind
     self.ring_z[ids, pos, :m] = z
     self.ring_R[ids, pos, :m, :m] = R
@@ -178,7 +191,11 @@ class RewindingScheduler(RaggedScheduler):
         idx = ((tl <= lt[:, None]) & valid).sum(1)                       # bisect_right(rewind_t, t), >= 1 here
         src = phys.gather(1, (idx - 1)[:, None])[:, 0]
         self.e.x[lf] = self.ring_x[lf, src]                              # ekf_sym.py:425-427
-        self.e.P[lf] = self.ring_P[lf, src]
+        if self.packed:
+          E = self.e.P.shape[1]
+          self.e.P[lf] = self.ring_P[lf, src][:, self._unpack].reshape(-1, E, E)
+        else:
+          self.e.P[lf] = self.ring_P[lf, src]
         self.t_filter[lf] = self.ring_t[lf, src]
         # the observations rewound over (logical idx .. cnt-1), copied out before the ring is reused
         n_rep = cnt - idx

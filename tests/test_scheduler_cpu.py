@@ -72,7 +72,7 @@ class _OracleEngine:
     return torch.as_tensor(y).reshape(n, 1, -1)
 
 
-def _run_rewinding_case(oracle_dir, depth, monkeypatch, seed):
+def _run_rewinding_case(oracle_dir, depth, monkeypatch, seed, packed=False):
   import rednose_b200.ekf_sym as drv
   from rednose_b200.filters.live import LiveKalman
   from rednose_b200.scheduler import RewindingScheduler
@@ -85,7 +85,7 @@ def _run_rewinding_case(oracle_dir, depth, monkeypatch, seed):
   Rk = {3: np.array([[0.2**2]]), 4: np.eye(3) * 0.025**2, 10: np.eye(3) * 0.5**2, 12: np.eye(3) * 25.0}
   refs = [drv.EKF_sym(oracle_dir, "live", LiveKalman.Q, x0[b], P0[b], 23, 22, quaternion_idxs=[3], max_rewind_age=0.5) for b in range(B)]
   eng = _OracleEngine(Oracle(oracle_dir, "live"), x0, P0, LiveKalman.Q, [3], flags=2)    # python-driver semantics: normalise after the update only
-  s = RewindingScheduler(eng, zd, depth=depth, max_rewind_age=0.5)
+  s = RewindingScheduler(eng, zd, depth=depth, max_rewind_age=0.5, packed=packed)
   ref_dropped = 0
   for tick in range(70):
     now = 0.01 * (tick + 1)
@@ -125,3 +125,9 @@ def test_rewinding_scheduler_with_a_short_ring(oracle_dir, monkeypatch):
   """depth 4: the ring wraps many times, rewinds reach its oldest entry and observations older than it are ignored."""
   s = _run_rewinding_case(oracle_dir, 4, monkeypatch, seed=11)
   assert s.rewinds > 5 and s.dropped > 5
+
+
+def test_rewinding_scheduler_with_packed_covariance_snapshots(oracle_dir, monkeypatch):
+  """packed=True: the ring holds lower triangles (half the memory); same results to the tolerance of the unpacked run."""
+  s = _run_rewinding_case(oracle_dir, 64, monkeypatch, seed=7, packed=True)
+  assert s.ring_P.shape[-1] == 22 * 23 // 2 and s.rewinds > 10 and s.replayed > s.rewinds
