@@ -222,6 +222,36 @@ def run_gpu(args):
     per_kind.setdefault(sched[args.warmup + j], []).append(ev[j][0].elapsed_time(ev[j][1]))
   assert bool(torch.isfinite(eng.x).all()), "filter diverged during the benchmark"
 
+  # ---- the same K steps captured once into a CUDA graph and replayed (one driver call for the whole loop) ----
+  graph_line = None
+  try:
+    x_keep, P_keep = eng.x.clone(), eng.P.clone()
+    def k_steps():
+      for j in range(args.steps):
+        one_step(args.warmup + j, sched[args.warmup + j])
+    g = eng.capture(k_steps)
+    eng.x.copy_(x_keep); eng.P.copy_(P_keep)
+    sync_all()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g.replay()                                   # warm
+    eng.x.copy_(x_keep); eng.P.copy_(P_keep)
+    sync_all()
+    g0.record()
+    g.replay()
+    g1.record()
+    sync_all()
+    g_ms = g0.elapsed_time(g1)
+    if world > 1:
+      tmax = torch.tensor([g_ms], dtype=torch.float64, device=dev)
+      dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+      g_ms = float(tmax.item())
+    graph_line = {"value": B * args.steps * world / (g_ms * 1e-3), "unit": "steps/s", "ms_per_step": g_ms / args.steps,
+                  "what": f"the same {args.steps} steps (observation refresh + fused launch each) captured into ONE CUDA graph (BatchedEKF.capture) and replayed"}
+    assert bool(torch.isfinite(eng.x).all())
+    del g
+  except Exception as ex:  # pylint: disable=broad-except
+    graph_line = {"error": repr(ex)[:200]}
+
   # ---- sustained figure: the same loop for >= args.sustain seconds (power-capped clocks, not a burst) ----
   sustained = None
   if args.sustain > 0:
@@ -438,6 +468,8 @@ def run_gpu(args):
       line["final_gather_what"] = f"NCCL all-gather of x [{world * B}, {dim}] ({world * B * dim * 8 / 1e6:.0f} MB) and of P [{world * B}, {edim}, {edim}] ({world * B * edim * edim * 8 / 1e9:.2f} GB, in slices)"
     if sustained is not None:
       line["sustained"] = sustained
+    if graph_line is not None:
+      line["cuda_graph_replay"] = graph_line
     line["numa_node"] = numa_node
     line["timed_region"] = f"{args.steps} steps = {elapsed_ms:.1f} ms: a burst figure; 'sustained' repeats the loop for >= {args.sustain} s"
     if not args.no_cpu_baseline:

@@ -743,3 +743,32 @@ def test_full_size_1m_kinematic_sampled_oracle(gen_dir, oracle_dir):
   assert rel_err(gx[sel], xr) < TIGHT and rel_err(gP[sel], Pr) < TIGHT
   assert np.isfinite(gx).all() and np.all(gP[:, 0, 0] > 0) and np.all(gP[:, 1, 1] > 0)
   assert float(np.max(np.abs(gP[:, 0, 1] - gP[:, 1, 0]))) < 1e-12
+
+
+def test_cuda_graph_replay_equals_eager_stepping(gen_dir, oracle_dir):
+  """BatchedEKF.capture: a captured sequence of fused steps (live, kinds 4 / 10 / 12; kinematic) replays bit-identically."""
+  o = Oracle(oracle_dir, "live")
+  B = 3000
+  x, P, Qm = live_batch(B, seed=410)
+  kinds = [12, 4, 10, 4, 10, 4]
+  zs = {k: live_obs(o, k, x[:64], seed=20 + k) for k in set(kinds)}
+  zd = {k: torch.as_tensor(np.tile(zs[k][0], (B // 64 + 1, 1))[:B]).cuda() for k in zs}
+  Rd = {k: torch.as_tensor(np.diag(np.diag(zs[k][1][0]))).cuda() for k in zs}
+  dt = torch.full((B,), 0.01, dtype=torch.float64, device="cuda")
+
+  def run(e, zw):
+    for k in kinds:
+      zw[k][:, 0, :].copy_(zd[k])
+      e.step(k, dt, zw[k], Rd[k])
+
+  e1 = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  e2 = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  zw1 = {k: torch.empty(B, 1, 3, dtype=torch.float64, device="cuda") for k in zs}
+  zw2 = {k: torch.empty(B, 1, 3, dtype=torch.float64, device="cuda") for k in zs}
+  run(e1, zw1); run(e1, zw1)
+  x0, P0 = e2.x.clone(), e2.P.clone()
+  g = e2.capture(lambda: run(e2, zw2))
+  e2.x.copy_(x0); e2.P.copy_(P0)
+  g.replay(); g.replay()
+  torch.cuda.synchronize()
+  assert torch.equal(e1.x, e2.x) and torch.equal(e1.P, e2.P) and all(torch.equal(zw1[k], zw2[k]) for k in zs)
