@@ -62,7 +62,7 @@ def gpu_numa_cpus(device_index: int):
       a, _, b = part.partition("-")
       cpus.extend(range(int(a), int(b or a) + 1))
     return node, sorted(cpus)
-  except (OSError, ValueError, AttributeError, RuntimeError):
+  except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
     return None, None
 
 

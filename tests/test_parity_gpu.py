@@ -772,3 +772,29 @@ def test_cuda_graph_replay_equals_eager_stepping(gen_dir, oracle_dir):
   g.replay(); g.replay()
   torch.cuda.synchronize()
   assert torch.equal(e1.x, e2.x) and torch.equal(e1.P, e2.P) and all(torch.equal(zw1[k], zw2[k]) for k in zs)
+
+
+def test_host_streamer_selected_columns_and_decimation(gen_dir):
+  """HostStreamer(out_cols=..., every=...): only the asked-for state columns come back, and only every `every`-th step;
+  the filter itself is unaffected (same P and x as direct stepping)."""
+  from rednose_b200.streaming import HostStreamer
+  B, T = 2053, 6
+  x, P, Qm = live_batch(B, seed=93)
+  rng = np.random.default_rng(4)
+  R4 = torch.as_tensor(np.diag([0.025**2] * 3)).cuda()
+  zs = [torch.as_tensor(rng.normal(0, 0.01, (B, 3))).pin_memory() for _ in range(T)]
+  a = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  b = _engine(gen_dir, "live", x, P, Qm, quaternion_idxs=[3])
+  cols = [0, 1, 2, 3, 4, 5, 6]
+  st = HostStreamer(b, {4: 3}, out_cols=cols, every=2)
+  a.filter_time = b.filter_time = 0.0
+  for k, z in enumerate(zs):
+    t = 0.01 * (k + 1)
+    xa, ya = a.predict_and_update_batch(t, 4, z, R4)
+    tk = st.submit(t, 4, z, R4)
+    xh, yh = st.result(tk, 4)
+    assert xh.shape == (B, 7) and torch.equal(yh, ya.cpu()[:, 0])
+    if k % 2 == 0:
+      assert torch.equal(xh, xa.cpu()[:, cols])
+  assert torch.equal(a.P, b.P) and torch.equal(a.x, b.x)
+  assert st.d2h_bytes == 8 * B * (7 * 3 + 3 * T)

@@ -58,3 +58,17 @@ def test_sharded_step_plus_gather_equals_single_process(oracle_dir, world, total
     p.join(timeout=60)
     assert p.exitcode == 0
   assert ok_x and ok_P and shape == (total, 2)
+
+
+def test_numa_binding_is_a_no_op_without_a_gpu():
+  """bind_to_gpu_numa must never break a process that has no (visible) GPU or no NUMA information: it returns None and
+  leaves the affinity mask alone."""
+  import os
+  import torch
+  from rednose_b200.sharding import bind_to_gpu_numa, gpu_numa_cpus
+  if torch.cuda.is_available():
+    import pytest
+    pytest.skip("a GPU is present")
+  before = os.sched_getaffinity(0)
+  assert gpu_numa_cpus(0) == (None, None) and bind_to_gpu_numa(0) is None
+  assert os.sched_getaffinity(0) == before
