@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(cta_threads<M>(), RNB_CTA_MIN_BLOCKS) ekf_step
   const PackedCol pc{s.Ppk, own ? col : 0, own ? col * (col + 1) / 2 : 0};
 
   // ---- stage: lower triangle of the covariance (the matrix is symmetric: half the read traffic), leaf values.
-  //      Warp w takes rows w, w + nw, ...; lanes run along the row (coalesced); RB rows are in flight per round trip. ----
+  //      Warp w takes rows w, w + nw, ...; lanes run along the row (coalesced). ----
   const int lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
   constexpr int NC = (E + 31) / 32;     // 32-column chunks of a row
   // cp.async (LDGSTS, 8 bytes per element: a packed row starts 16-byte aligned only every other row): no registers are
