@@ -577,7 +577,8 @@ def run_rts(args):
     return 0.01 * (k + 1), sched[k], zslot[slot][lo:hi], Rk[sched[k]]
 
   cs = CheckpointedSmoother(d, "live", Q, dim, edim, quaternion_idxs=quat, device=dev, hbm_budget_bytes=int(args.hbm_budget_gb) << 30, segment=S)
-  tile = min(cs.tile_size(T), B)
+  tile, _ntiles = cs.plan(B, T)
+  cs.tile = tile            # the warm-up run (shorter history) must use the same tiles as the timed run
   # smoothed pose columns go back to pinned host memory, segment by segment (the result a caller keeps; P stays on the device)
   pose_cols = 7
   # two slots: the device-to-host copy of one segment's poses runs on a side stream under the next segment's kernels

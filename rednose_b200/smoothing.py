@@ -102,13 +102,20 @@ class CheckpointedSmoother:
   def tile_size(self, T):
     return self.tile or max(1, int(self.budget // self.bytes_per_filter(T)))
 
+  def plan(self, B, T):
+    """(filters per tile, tiles): the batch is cut into EQUAL tiles no larger than tile_size(T), so that one engine and
+    one set of history / checkpoint buffers serve every tile."""
+    cap = min(self.tile_size(T), B)
+    ntiles = (B + cap - 1) // cap
+    return (B + ntiles - 1) // ntiles, ntiles
+
   def run(self, x0, P0, T, obs_fn, sink, norm_quats=False, t0=0.0):
     """obs_fn(k, lo, hi) -> (t, kind, z, R) must return the SAME observation every time it is asked for step k (each step
     is filtered twice) in a buffer the kernel may overwrite.  sink(lo, hi, k0, xs [n, tile, DIM], Ps [n, tile, EDIM, EDIM])
     receives the smoothed steps k0 .. k0 + n - 1 of filters lo..hi (segments arrive last to first; views valid during
     the call only).  Returns the number of tiles."""
     B, S = x0.shape[0], self.segment
-    n_tile = min(self.tile_size(T), B)
+    n_tile, _ = self.plan(B, T)
     nseg = (T + S - 1) // S
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     fwd_ms = refwd_ms = bwd_ms = 0.0
@@ -117,6 +124,7 @@ class CheckpointedSmoother:
       hi = min(lo + n_tile, B)
       n = hi - lo
       if self._engine is None or self._engine.B != n:
+        self._engine = self._hist = self._ck = self._term = None   # release the previous tile's buffers before allocating
         self._engine = BatchedEKF(self.folder, self.name, self.Q, x0[lo:hi], P0[lo:hi], device=self.device, quaternion_idxs=self.quat)
         self._hist = self._engine.new_history(S + 1)
         self._ck = (torch.empty(nseg, n, self.dim_x, dtype=torch.float64, device=self.device),

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 N=${1:-8}; T=${2:-1000}
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --workload live_rts --rts-steps $T --steps 2 > gpurun_out/r02_n${N}_live_rts.json 2> gpurun_out/r02_n${N}_live_rts.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --workload live_rts --rts-steps $T --steps ${3:-2} > gpurun_out/r02_n${N}_live_rts.json 2> gpurun_out/r02_n${N}_live_rts.err
 tail -3 gpurun_out/r02_n${N}_live_rts.err; python - <<PY
 import json
 d=json.loads(open('gpurun_out/r02_n${N}_live_rts.json').read().strip().split('\n')[-1])
