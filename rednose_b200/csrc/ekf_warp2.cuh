@@ -284,6 +284,11 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
       {
         const int fn = f + 2 * NST;
         const long long fa = fid_of(fn < ng ? fn : 0), fb = fid_of(fn + 1 < ng ? fn + 1 : 0);
+        // WAR across proxies: the 128-bit shared loads above are generic-proxy reads that may still be queued when this
+        // point is reached (a load is "issued", not "performed"); the bulk copy that refills the slot writes through the
+        // async proxy.  The proxy fence orders the reads before it -- without it about one filter-step in 1e7 saw the last
+        // tile rows of the NEXT pair (found as run-to-run differences of 10 000-step histories, scripts/dbg_rts_race.py).
+        fence_async_smem();
         __syncwarp();   // every lane holds its columns before the slot is refilled
         if (lane == 0 && fn < ng) issue_pair(fn, slot, fa, fb);
       }
