@@ -289,6 +289,10 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
         // async proxy.  The proxy fence orders the reads before it -- without it about one filter-step in 1e7 saw the last
         // tile rows of the NEXT pair (found as run-to-run differences of 10 000-step histories, scripts/dbg_rts_race.py).
         fence_async_smem();
+        {   // ... and one instruction that depends on the LAST load of the sequence (shared-memory loads of a warp return in order)
+          const double landed = p0[E - 1] + p1[E - 1];
+          asm volatile("" ::"d"(landed));
+        }
         __syncwarp();   // every lane holds its columns before the slot is refilled
         if (lane == 0 && fn < ng) issue_pair(fn, slot, fa, fb);
       }
