@@ -815,18 +815,17 @@ def test_forward_filter_is_bit_reproducible_run_to_run(gen_dir):
        12: (e.x[:, :3] + torch.as_tensor(rng.normal(0, 3.0, (B, 3))).cuda())[None].repeat(2, 1, 1)}
   R = {4: torch.eye(3, dtype=torch.float64, device="cuda") * 0.025**2, 10: torch.eye(3, dtype=torch.float64, device="cuda") * 0.25,
        12: torch.eye(3, dtype=torch.float64, device="cuda") * 25.0}
-  hist = e.new_history(T)
-
   def run():
-    e.x.copy_(x0); e.P.copy_(P0); e.filter_time = 0.0; hist.n = 0
+    e.x.copy_(x0); e.P.copy_(P0)
     for k in range(T):
       kind = 12 if k % 50 == 0 else (4 if k % 2 else 10)
-      e.step_recorded(hist, kind, 0.01 * (k + 1), z[kind][k % 2].clone(), R[kind])
-    return e.x.clone(), e.P.clone(), hist.P_pred.clone(), hist.P_filt.clone()
+      e.step(kind, 0.01, z[kind][k % 2].clone(), R[kind])
+    return e.x.clone(), e.P.clone()
 
+  torch.cuda.empty_cache()
   ref = run()
   assert bool(torch.isfinite(ref[1]).all())
   for r in range(5):
     got = run()
-    for name, a, b in zip(("x", "P", "P_pred history", "P_filt history"), ref, got):
+    for name, a, b in zip(("x", "P"), ref, got):   # a glitch anywhere changes the rest of that filter's trajectory
       assert torch.equal(a, b), (r, name, (a != b).nonzero()[0].tolist())
