@@ -29,7 +29,7 @@ def nvcc_path():
 
 TUNE_ENV = ("REDNOSE_B200_GROUP", "REDNOSE_B200_WARPS", "REDNOSE_B200_TMA", "REDNOSE_B200_STAGES", "REDNOSE_B200_TMA_STORE", "REDNOSE_B200_SMALLSYM",
             "REDNOSE_B200_RTS_MMA", "REDNOSE_B200_MIN_WARPS", "REDNOSE_B200_PAIR", "REDNOSE_B200_PAIR_GROUP", "REDNOSE_B200_PAIR_MIN_WARPS",
-            "REDNOSE_B200_RTS_MIN_CTAS", "REDNOSE_B200_CTA_MIN_BLOCKS", "REDNOSE_B200_MAXRREG")
+            "REDNOSE_B200_RTS_MIN_CTAS", "REDNOSE_B200_CTA_MIN_BLOCKS", "REDNOSE_B200_PAIR_WAR_FIX", "REDNOSE_B200_PAIR_LATE_REFILL", "REDNOSE_B200_MAXRREG")
 
 
 def _flags_match(folder, name):
@@ -72,7 +72,7 @@ def compile_filter(folder, name, force=False, verbose=False):
 
 
 def _compile_filter_locked(folder, name, src, lib, verbose):
-  tune = [f"-D{k}={os.environ[e]}" for k, e in (("RNB_GROUP", "REDNOSE_B200_GROUP"), ("RNB_WARPS", "REDNOSE_B200_WARPS"), ("RNB_TMA", "REDNOSE_B200_TMA"), ("RNB_STAGES", "REDNOSE_B200_STAGES"), ("RNB_TMA_STORE", "REDNOSE_B200_TMA_STORE"), ("RNB_SMALLSYM", "REDNOSE_B200_SMALLSYM"), ("RNB_RTS_MMA", "REDNOSE_B200_RTS_MMA"), ("RNB_MIN_WARPS", "REDNOSE_B200_MIN_WARPS"), ("RNB_PAIR", "REDNOSE_B200_PAIR"), ("RNB_PAIR_GROUP", "REDNOSE_B200_PAIR_GROUP"), ("RNB_PAIR_MIN_WARPS", "REDNOSE_B200_PAIR_MIN_WARPS"), ("RNB_RTS_MIN_CTAS", "REDNOSE_B200_RTS_MIN_CTAS"), ("RNB_CTA_MIN_BLOCKS", "REDNOSE_B200_CTA_MIN_BLOCKS")) if os.environ.get(e)]
+  tune = [f"-D{k}={os.environ[e]}" for k, e in (("RNB_GROUP", "REDNOSE_B200_GROUP"), ("RNB_WARPS", "REDNOSE_B200_WARPS"), ("RNB_TMA", "REDNOSE_B200_TMA"), ("RNB_STAGES", "REDNOSE_B200_STAGES"), ("RNB_TMA_STORE", "REDNOSE_B200_TMA_STORE"), ("RNB_SMALLSYM", "REDNOSE_B200_SMALLSYM"), ("RNB_RTS_MMA", "REDNOSE_B200_RTS_MMA"), ("RNB_MIN_WARPS", "REDNOSE_B200_MIN_WARPS"), ("RNB_PAIR", "REDNOSE_B200_PAIR"), ("RNB_PAIR_GROUP", "REDNOSE_B200_PAIR_GROUP"), ("RNB_PAIR_MIN_WARPS", "REDNOSE_B200_PAIR_MIN_WARPS"), ("RNB_RTS_MIN_CTAS", "REDNOSE_B200_RTS_MIN_CTAS"), ("RNB_CTA_MIN_BLOCKS", "REDNOSE_B200_CTA_MIN_BLOCKS"), ("RNB_PAIR_WAR_FIX", "REDNOSE_B200_PAIR_WAR_FIX"), ("RNB_PAIR_LATE_REFILL", "REDNOSE_B200_PAIR_LATE_REFILL")) if os.environ.get(e)]
   if os.environ.get("REDNOSE_B200_MAXRREG"):
     tune += ["-maxrregcount", os.environ["REDNOSE_B200_MAXRREG"]]
   tmp = lib + f".tmp{os.getpid()}"

@@ -404,7 +404,6 @@ __global__ void __launch_bounds__(W * 32, RNB_MIN_WARPS / W) ekf_step_warp(const
           // keeping NST bulk loads in flight per warp
           const long long nfid = fid_of(f + NST < ng ? f + NST : 0);
           fence_async_smem();   // generic-proxy reads of the tile ordered before the async-proxy refill (see ekf_warp2.cuh)
-          { const double landed = p[E - 1] + p[E - 2]; asm volatile("" ::"d"(landed)); }
           __syncwarp();   // every lane has read its column before the slot is overwritten
           if (lane == 0 && f + NST < ng) issue_load(nfid, slot);
         }

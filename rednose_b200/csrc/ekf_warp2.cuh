@@ -34,6 +34,12 @@ namespace rnb {
 #ifndef RNB_PAIR_FV_EARLY
 #define RNB_PAIR_FV_EARLY 0    // 1: F value slots are fetched before the tile wait instead of after it
 #endif
+#ifndef RNB_PAIR_WAR_FIX
+#define RNB_PAIR_WAR_FIX 1   // ordering of the tile reads before the slot refill: 1 = proxy fence (deterministic over 250 x 6.3e6 filter-steps), 2 = wait on the last load only (NOT sufficient: 66 of 250 runs differed), 3 = both
+#endif
+#ifndef RNB_PAIR_LATE_REFILL
+#define RNB_PAIR_LATE_REFILL 0   // 1: in fused-predict instantiations the fence + refill move behind the exchange stores of F P (the tile loads have long landed there)
+#endif
 #ifndef RNB_PAIR_TMA_STAGE
 #define RNB_PAIR_TMA_STAGE 1   // x / z / R / dt blocks of a full group arrive by bulk copy (one mbarrier wait, no registers held)
 #endif
@@ -281,15 +287,16 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
         const double2 t = *reinterpret_cast<const double2*>(tile + i * E + c0);
         p0[i] = t.x; p1[i] = t.y;
       }
-      {
-        const int fn = f + 2 * NST;
-        const long long fa = fid_of(fn < ng ? fn : 0), fb = fid_of(fn + 1 < ng ? fn + 1 : 0);
+      const int fn = f + 2 * NST;
+      const long long fa = fid_of(fn < ng ? fn : 0), fb = fid_of(fn + 1 < ng ? fn + 1 : 0);
+      constexpr bool LATE = RNB_PAIR_LATE_REFILL && (M::NFROWS > 0);
+      if (!(LATE && do_pred)) {
         // WAR across proxies: the 128-bit shared loads above are generic-proxy reads that may still be queued when this
         // point is reached (a load is "issued", not "performed"); the bulk copy that refills the slot writes through the
         // async proxy.  The proxy fence orders the reads before it -- without it about one filter-step in 1e7 saw the last
         // tile rows of the NEXT pair (found as run-to-run differences of 10 000-step histories, scripts/dbg_rts_race.py).
-        fence_async_smem();
-        {   // ... and one instruction that depends on the LAST load of the sequence (shared-memory loads of a warp return in order)
+        if constexpr (RNB_PAIR_WAR_FIX & 1) fence_async_smem();
+        if constexpr (RNB_PAIR_WAR_FIX & 2) {   // experiment kept for the record: waiting on the LAST load of the sequence is NOT enough
           const double landed = p0[E - 1] + p1[E - 1];
           asm volatile("" ::"d"(landed));
         }
@@ -320,7 +327,9 @@ __global__ void __launch_bounds__(32, RNB_PAIR_MIN_WARPS) ekf_step_pair(const St
               }
             }
           }
+          if constexpr (LATE) fence_async_smem();   // late refill: the tile loads landed long ago, the fence costs nothing here
           __syncwarp();
+          if constexpr (LATE) { if (lane == 0 && fn < ng) issue_pair(fn, slot, fa, fb); }
           // a column whose index is a non-identity row of F is replaced by that row of F P (symmetry gives the rest)
           if ((M::FROW_MASK >> c0) & 1u) {
             const double* xr = exh + SC::exrow(__popc(M::FROW_MASK & ((1u << c0) - 1u)));
